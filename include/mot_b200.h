@@ -1,0 +1,162 @@
+/* mot_b200.h -- C ABI of the B200-native LiDAR tracker hot path (libmot_b200.so).
+ *
+ * The reference (MLCS-Yonsei/multiple-object-tracking-lidar) has no plugin/FFI interface; the drop-in
+ * boundary is the set of C++ call sites inside ObstacleTrack::clusterPointCloud and callIHGP.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference repository;
+ * MOT.cpp = src/multiple_object_tracking_lidar.cpp, MOT.h = include/multiple_object_tracking_lidar/
+ * multiple_object_tracking_lidar.h, IHGP.cpp/.hpp = src/ihgp/InfiniteHorizonGP.cpp and its header).
+ * include/mot_b200_pcl.hpp is the header-only C++ adapter that keeps those call sites source compatible.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary; nothing throws.
+ *   - every function returns an int status: 0 = MOT_OK, negative = error (mot_last_error gives the text).
+ *   - points are arrays of 4 floats (x, y, z, pad) == the memory layout of pcl::PointXYZ, so
+ *     &cloud.points[0] is passed as-is ("xyz16").
+ *   - input buffers are caller owned and only read; output buffers are caller owned, capacities are
+ *     passed in elements; all device memory is owned by the handle.
+ *   - calls block until their outputs are host visible (the reference consumes results synchronously on
+ *     the ROS spinner thread, MOT.cpp:117-121).  A handle is not re-entrant; use one handle per
+ *     thread / stream / GPU.
+ *   - there is no CPU fallback: without a CUDA device mot_create fails with MOT_ERR_CUDA.
+ */
+#ifndef MOT_B200_H_
+#define MOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mot_handle mot_handle;
+
+enum {
+    MOT_OK = 0,
+    MOT_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, tolerance <= 0, ...) */
+    MOT_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    MOT_ERR_CAPACITY = -3,  /* input larger than the handle's max_points / output buffer too small */
+    MOT_ERR_NO_MAP = -4,    /* removeStatic requested before mot_set_map (reference: map_init, MOT.cpp:128) */
+    MOT_ERR_STATE = -5,     /* result query without a preceding clustering call / IHGP not configured */
+    MOT_ERR_NONFINITE = -6  /* NaN/Inf coordinate in a cloud passed to clustering (reference assumes is_dense) */
+};
+
+/* Per-cluster table row (north_star: centroid / bbox per cluster; 40 bytes). */
+typedef struct mot_cluster_stat {
+    int32_t count;      /* number of points */
+    float mean[3];      /* arithmetic centroid (pcl::compute3DCentroid semantics, MOT.h:62) */
+    float bbox_min[3];
+    float bbox_max[3];
+} mot_cluster_stat;
+
+/* Stage timings of the last frame call, milliseconds of GPU time (CUDA events). */
+typedef struct mot_timings {
+    float remove_static_ms;
+    float grid_build_ms;    /* keys + radix sort + reorder + cell tables */
+    float union_find_ms;    /* neighbour test + hooking + pointer jumping */
+    float cluster_table_ms; /* size filter, ordering, CSR emission */
+    float reduce_ms;        /* segmented reduction + circumcentre */
+    float total_ms;
+} mot_timings;
+
+const char* mot_version(void);
+
+/* Opaque handle owning device workspace, stream and pinned staging for up to max_points points per
+ * frame (or per frame batch) and max_tracks IHGP tracks. */
+int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** out);
+int mot_destroy(mot_handle* h);
+const char* mot_last_error(mot_handle* h);
+
+/* Replaces ObstacleTrack::mapCallback (MOT.cpp:235-251): occ is nav_msgs/OccupancyGrid.data, row-major
+ * height x width, -1 unknown, 0..100 occupancy; resolution/origin/orientation are MapMetaData.
+ * static_tolerance is the launch parameter `static_tolarance`, clamped to [0,4] (MOT.cpp:95-96).
+ * Builds the dilated "blocked" bitmap once so that removeStatic is one bit lookup per point. */
+int mot_set_map(mot_handle* h, const int8_t* occ, int width, int height, float resolution, double origin_x,
+                double origin_y, const double quat_xyzw[4], int static_tolerance);
+
+/* Launch parameters cluster_tolerance / min_cluster_size / max_cluster_size
+ * (MOT.cpp:90-92 -> ec.setClusterTolerance / setMinClusterSize / setMaxClusterSize, MOT.cpp:481-483). */
+int mot_set_cluster_params(mot_handle* h, float cluster_tolerance, int min_cluster_size, int max_cluster_size);
+
+/* Replaces ObstacleTrack::removeStatic (MOT.cpp:664-706; decl MOT.h:182).  Kept points are written in
+ * input order.  out_xyz16 may alias nothing in xyz16.  *m receives the number kept. */
+int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xyz16, size_t out_capacity, size_t* m);
+
+/* Replaces pcl::search::KdTree::setInputCloud + pcl::EuclideanClusterExtraction::extract
+ * (MOT.cpp:472-488).  Output is the CSR form of std::vector<pcl::PointIndices>: cluster c owns
+ * point_indices[cluster_offsets[c] .. cluster_offsets[c+1]), indices ascending inside a cluster (PCL sorts
+ * them), clusters ordered by size descending (PCL's extract()), ties by smallest index ascending.
+ * Components with fewer than min or more than max points are dropped whole. */
+int mot_cluster(mot_handle* h, const float* xyz16, size_t m, int32_t* cluster_offsets, size_t offsets_capacity,
+                int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters);
+
+/* Per-cluster count / mean / bbox of the clusters found by the last mot_cluster / mot_frame call. */
+int mot_cluster_stats(mot_handle* h, mot_cluster_stat* stats, size_t capacity);
+
+/* Replaces ObstacleTrack::getCentroid (MOT.cpp:708-822; decl MOT.h:184-187) for the clusters of the last
+ * mot_cluster / mot_frame call: farthest pair, farthest point from its XY line, XY circumcentre.
+ * out_xyzi: n_clusters x 4 floats (x, y, z = 0, intensity = stamp_minus_time_init), i.e. the payload of
+ * the pcl::PointXYZI the reference returns. */
+int mot_get_centroid(mot_handle* h, double stamp_minus_time_init, float* out_xyzi, size_t capacity);
+
+/* Fused frame step: removeStatic -> clustering -> table (+ optional circumcentres) without host round trips
+ * of the cloud (ObstacleTrack::clusterPointCloud minus VoxelGrid, MOT.cpp:461-491).
+ * Optional outputs may be NULL: kept_xyz16 (capacity kept_capacity points), stats, centroids_xyzi
+ * (both with table_capacity rows).  Indices refer to positions in the kept cloud, as in the reference. */
+int mot_frame(mot_handle* h, const float* xyz16, size_t n, double stamp_minus_time_init, float* kept_xyz16,
+              size_t kept_capacity, size_t* m, int32_t* cluster_offsets, size_t offsets_capacity,
+              int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats,
+              float* centroids_xyzi, size_t table_capacity);
+
+/* ---- device-resident entry points (inputs already in HBM; used by bench.py's `value` leg and by callers that
+ * keep the cloud on the GPU).  d_xyz16 is a device pointer on the handle's device.  Results stay on the
+ * device; only the 64-byte result header crosses PCIe.  do_remove_static = 0 clusters the cloud as is. */
+int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remove_static, int with_centroids,
+                     double stamp_minus_time_init);
+/* Counts of the last result: kept points, clusters, total indices. */
+int mot_result_counts(mot_handle* h, size_t* m, int32_t* n_clusters, size_t* n_indices);
+/* Device pointers of the last result (valid until the next call on the handle). */
+int mot_result_device_ptrs(mot_handle* h, const float** d_kept_xyz16, const int32_t** d_cluster_offsets,
+                           const int32_t** d_point_indices, const mot_cluster_stat** d_stats,
+                           const float** d_centroids_xyzi);
+/* Copies the last result to host buffers (any may be NULL). */
+int mot_result_fetch(mot_handle* h, float* kept_xyz16, size_t kept_capacity, int32_t* cluster_offsets,
+                     size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity,
+                     mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity);
+/* Component label of every kept point after union-find (smallest point index of its component; no size
+ * filter).  Debug/parity aid for partition checks at sizes where CSR comparison is unwieldy. */
+int mot_result_labels(mot_handle* h, int32_t* labels, size_t capacity);
+int mot_last_timings(mot_handle* h, mot_timings* t);
+
+/* Pins / unpins a caller-owned host buffer so copies run at full PCIe speed (optional). */
+int mot_host_register(void* ptr, size_t bytes);
+int mot_host_unregister(void* ptr);
+
+/* ---- frame batches (BASELINE config 3: multi-LiDAR / multi-sequence streams).  n_frames clouds are
+ * concatenated in xyz16; frame f owns points [frame_offsets[f], frame_offsets[f+1]).  Frames never share
+ * clusters.  cluster c belongs to frame f iff frame_cluster_offsets[f] <= c < frame_cluster_offsets[f+1];
+ * point_indices are positions inside the owning frame's cloud.  No removeStatic (apply it per frame). */
+int mot_cluster_batch(mot_handle* h, const float* xyz16, const int64_t* frame_offsets, int n_frames,
+                      int32_t* frame_cluster_offsets /* n_frames+1 */, int32_t* cluster_offsets,
+                      size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters);
+int mot_cluster_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames);
+
+/* ---- IHGP track filter.  Replaces Matern32model + InfiniteHorizonGP construction in
+ * registerNewObstacle (MOT.cpp:521-534; IHGP.cpp:12-37; M32.cpp:15-24): hyp = {sigma2, magnSigma2,
+ * lengthScale} already exponentiated as at MOT.cpp:524-530; dt = dt_gp = 1/frequency (MOT.cpp:159);
+ * data_length = launch parameter data_length (MOT.cpp:113). */
+int mot_ihgp_configure(mot_handle* h, double dt, float lpf_tau, const double hyp_x[3], const double hyp_y[3],
+                       int data_length);
+/* 16 doubles per axis: A[4], AKHA[4], K[2], G[4], S, lambda (row-major 2x2); axis 0 = x, 1 = y. */
+int mot_ihgp_constants(mot_handle* h, int axis, double* consts16);
+/* Replaces the per-track loop of ObstacleTrack::callIHGP (MOT.cpp:621-662): LPF_pos (MOT.cpp:824-833),
+ * IHGP_fixed_vel (MOT.cpp:871-920) = init_step + (L-1) x update + getEft (IHGP.cpp:108-196), +-1.5 m/s
+ * clamp (MOT.cpp:649-654).  rings: T x L x 4 floats (x, y, z, intensity=time), oldest sample first
+ * (stack_obj, MOT.h:107).  m_state: T x 4 doubles (m_x[2], m_y[2]), in/out -- the cross-frame carry the
+ * reference keeps inside each InfiniteHorizonGP object.  pos_vel: T x 8 floats (pos xyzi, vel xyzi). */
+int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_state, float* pos_vel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOT_B200_H_ */

@@ -1,0 +1,386 @@
+// cluster_table.cuh -- K6/K7/K8: component sizes, min/max-size filter, cluster ordering, CSR emission,
+// per-cluster segmented reduction (count / mean / bbox) and the reference's circumcentre "centroid".
+//
+// Output contract = std::vector<pcl::PointIndices> as the reference sees it after ec.extract()
+// (MOT.cpp:488): components outside [min,max] dropped whole, indices ascending inside a cluster, clusters by
+// size descending; ties (unspecified in PCL's std::sort) are pinned to smallest-index-first.
+#pragma once
+#include "common.cuh"
+#include "grid_uf.cuh"
+
+namespace mot {
+
+// Layout of the 64-bit cluster ordering key: frame | (size_cap - size) | local min index.
+struct ClusterKeyCodec {
+    int size_bits, idx_bits;  // frame occupies the bits above
+    unsigned size_cap;        // (1 << size_bits) - 1
+};
+__device__ __forceinline__ uint64_t ckey_make(const ClusterKeyCodec& c, int frame, int size, int local_min) {
+    return ((((uint64_t)frame << c.size_bits) | (uint64_t)(c.size_cap - (unsigned)size)) << c.idx_bits) | (uint64_t)local_min;
+}
+__device__ __forceinline__ int ckey_size(const ClusterKeyCodec& c, uint64_t k) {
+    return (int)(c.size_cap - (unsigned)((k >> c.idx_bits) & c.size_cap));
+}
+__device__ __forceinline__ int ckey_frame(const ClusterKeyCodec& c, uint64_t k) { return (int)(k >> (c.idx_bits + c.size_bits)); }
+
+// Component size and smallest original index, accumulated per fine cell (warp-aggregated so that the root of a
+// giant component is not hit by one atomic per cell).
+__global__ void __launch_bounds__(256) k_comp_accumulate(const int* __restrict__ fc_start, const int* __restrict__ root,
+                                                          int* __restrict__ csize, int* __restrict__ cmin,
+                                                          const int* __restrict__ d_counts) {
+    const int n_fine = d_counts[CNT_FINE];
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (n_fine + stride - 1) / stride;
+    for (int it = 0; it < rounds; ++it) {
+        const int c = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = c < n_fine;
+        const int r = valid ? root[c] : -1;
+        const int n = valid ? fc_start[c + 1] - fc_start[c] : 0;
+        const int mi = valid ? cmin[c] : 0x7fffffff;
+        const unsigned peers = __match_any_sync(kFull, r);
+        const int nsum = __reduce_add_sync(peers, n);
+        const int mmin = __reduce_min_sync(peers, mi);
+        if (valid && lane_id() == __ffs(peers) - 1) {
+            atomicAdd(&csize[r], nsum);
+            atomicMin(&cmin[r], mmin);
+        }
+    }
+}
+
+// Kept roots -> unordered list of (ordering key, root fine cell).  The sort that follows makes the order
+// deterministic (keys are unique: a point index belongs to one component).
+__global__ void __launch_bounds__(256) k_kept_list(const int* __restrict__ root, const int* __restrict__ csize, const int* __restrict__ cmin,
+                                                    const int* __restrict__ frame_offsets, int n_frames, int min_size, int max_size,
+                                                    ClusterKeyCodec kc, uint64_t* __restrict__ ckeys, uint32_t* __restrict__ croots,
+                                                    int* __restrict__ d_counts) {
+    const int n_fine = d_counts[CNT_FINE];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_fine; c += gridDim.x * blockDim.x) {
+        if (root[c] != c) continue;
+        const int s = csize[c];
+        if (s < min_size || s > max_size) continue;
+        const int mi = cmin[c];
+        int frame = 0, local = mi;
+        if (n_frames > 1) {
+            frame = frame_of(frame_offsets, n_frames, mi);
+            local = mi - frame_offsets[frame];
+        }
+        const int slot = atomicAdd(&d_counts[CNT_K], 1);
+        ckeys[slot] = ckey_make(kc, frame, s, local);
+        croots[slot] = (uint32_t)c;
+        atomicAdd(&d_counts[CNT_TOTAL], s);
+    }
+}
+
+// Small-K path: one CTA sorts up to CL_SMALL_MAX clusters with a bitonic network in shared memory, then emits
+// rank -> root, sizes and CSR offsets in the same launch.
+constexpr int CL_SMALL_MAX = 8192;
+constexpr int CL_SMALL_THREADS = 1024;
+constexpr size_t CL_SMALL_SMEM = (size_t)CL_SMALL_MAX * 12;  // dynamic: u64 keys + u32 roots
+
+__global__ void __launch_bounds__(CL_SMALL_THREADS) k_clusters_small(const uint64_t* __restrict__ ckeys_in, const uint32_t* __restrict__ croots_in,
+                                                                      int K, ClusterKeyCodec kc, uint64_t* __restrict__ ckeys_out,
+                                                                      int* __restrict__ crank, int* __restrict__ cl_offsets) {
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(cl_smem);
+    uint32_t* sr = reinterpret_cast<uint32_t*>(sk + CL_SMALL_MAX);
+    __shared__ int scratch[36];
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += CL_SMALL_THREADS) {
+        sk[i] = i < K ? ckeys_in[i] : ~0ull;
+        sr[i] = i < K ? croots_in[i] : 0u;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += CL_SMALL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const uint64_t a = sk[i], b = sk[ixj];
+                    if ((a > b) == up) {
+                        sk[i] = b; sk[ixj] = a;
+                        const uint32_t t = sr[i]; sr[i] = sr[ixj]; sr[ixj] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // sizes -> exclusive scan -> offsets; each thread owns a contiguous run of <= 8 clusters
+    const int per = (K + CL_SMALL_THREADS - 1) / CL_SMALL_THREADS;
+    const int s = threadIdx.x * per, e = min(K, s + per);
+    int local = 0;
+    for (int i = s; i < e; ++i) local += ckey_size(kc, sk[i]);
+    int total;
+    int run = block_exclusive_scan(local, scratch, &total);
+    for (int i = s; i < e; ++i) {
+        cl_offsets[i] = run;
+        run += ckey_size(kc, sk[i]);
+        crank[sr[i]] = i;
+        ckeys_out[i] = sk[i];
+    }
+    if (threadIdx.x == 0) cl_offsets[K] = total;
+}
+
+// Large-K path, after the 64-bit radix sort of (key, root): per-block size sums, then offsets + ranks.
+constexpr int CLF_THREADS = 256;
+constexpr int CLF_MAX_GRID = 592;
+__global__ void __launch_bounds__(CLF_THREADS) k_clusters_count(const uint64_t* __restrict__ ckeys, int K, int chunk, ClusterKeyCodec kc,
+                                                                 int* __restrict__ block_sums) {
+    __shared__ int red[CLF_THREADS / 32];
+    const int begin = blockIdx.x * chunk, end = min(K, begin + chunk);
+    int s = 0;
+    for (int i = begin + threadIdx.x; i < end; i += CLF_THREADS) s += ckey_size(kc, ckeys[i]);
+    s = warp_sum(s);
+    if (lane_id() == 0) red[warp_id()] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < CLF_THREADS / 32; ++w) t += red[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(CLF_THREADS) k_clusters_finalize(const uint64_t* __restrict__ ckeys, const uint32_t* __restrict__ croots, int K,
+                                                                    int chunk, ClusterKeyCodec kc, const int* __restrict__ block_sums,
+                                                                    int* __restrict__ crank, int* __restrict__ cl_offsets) {
+    __shared__ int scratch[36];
+    int base = block_prefix_of(block_sums, blockIdx.x, scratch);
+    const int begin = blockIdx.x * chunk, end = min(K, begin + chunk);
+    for (int tb = begin; tb < end; tb += CLF_THREADS) {
+        const int i = tb + threadIdx.x;
+        const int sz = i < end ? ckey_size(kc, ckeys[i]) : 0;
+        int total;
+        const int excl = block_exclusive_scan(sz, scratch, &total);
+        if (i < end) {
+            cl_offsets[i] = base + excl;
+            crank[croots[i]] = i;
+        }
+        base += total;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cl_offsets[K] = base;
+}
+
+// frame_cluster_offsets[f] = first cluster of frame f in the sorted order (batch mode; K+1 sentinel at F).
+__global__ void k_frame_cluster_offsets(const uint64_t* __restrict__ ckeys, int K, ClusterKeyCodec kc, int n_frames,
+                                        int* __restrict__ frame_cluster_offsets) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > n_frames) return;
+    int lo = 0, hi = K;  // first k with frame(k) >= f
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ckey_frame(kc, ckeys[mid]) < f) lo = mid + 1; else hi = mid;
+    }
+    frame_cluster_offsets[f] = lo;
+}
+
+// Cluster rank of every point, scattered back to original point order (key of the final stable partition),
+// plus the component label (smallest original index of the component) for partition checks.
+__global__ void __launch_bounds__(256) k_point_rank(const float4* __restrict__ spts, const int* __restrict__ pcell, const int* __restrict__ root,
+                                                     const int* __restrict__ crank, const int* __restrict__ cmin, int m, int K,
+                                                     uint32_t* __restrict__ pkey, int* __restrict__ labels) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int orig = __float_as_int(spts[j].w);
+    const int r = root[pcell[j]];
+    const int k = crank[r];
+    pkey[orig] = k < 0 ? (uint32_t)K : (uint32_t)k;
+    labels[orig] = cmin[r];
+}
+
+// Batch mode: turn global point indices into positions inside the owning frame.
+__global__ void __launch_bounds__(256) k_localize_indices(uint32_t* __restrict__ idx, int total, const int* __restrict__ frame_offsets, int n_frames) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int g = (int)idx[t];
+    idx[t] = (uint32_t)(g - frame_offsets[frame_of(frame_offsets, n_frames, g)]);
+}
+
+// ---- K7: segmented reduction, one CTA per cluster over its (ascending) index list -----------------------------
+struct ClusterStat {  // == mot_cluster_stat
+    int count;
+    float mean[3], bmin[3], bmax[3];
+};
+constexpr int STAT_THREADS = 128;
+__global__ void __launch_bounds__(STAT_THREADS) k_cluster_stats(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
+                                                                 const uint32_t* __restrict__ indices, int K, ClusterStat* __restrict__ out) {
+    __shared__ double ssum[STAT_THREADS / 32][3];
+    __shared__ float smin[STAT_THREADS / 32][3], smax[STAT_THREADS / 32][3];
+    for (int c = blockIdx.x; c < K; c += gridDim.x) {
+        const int s = cl_offsets[c], e = cl_offsets[c + 1];
+        double sum[3] = {0, 0, 0};
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int t = s + threadIdx.x; t < e; t += STAT_THREADS) {
+            const float4 p = pts[indices[t]];
+            sum[0] += (double)p.x; sum[1] += (double)p.y; sum[2] += (double)p.z;
+            mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+            mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sum[d] += __shfl_xor_sync(kFull, sum[d], o);
+                mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
+            }
+        __syncthreads();
+        if (lane_id() == 0)
+            for (int d = 0; d < 3; ++d) { ssum[warp_id()][d] = sum[d]; smin[warp_id()][d] = mn[d]; smax[warp_id()][d] = mx[d]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ClusterStat st;
+            st.count = e - s;
+            for (int d = 0; d < 3; ++d) {
+                double a = 0; float lo = INFINITY, hi = -INFINITY;
+                for (int w = 0; w < STAT_THREADS / 32; ++w) { a += ssum[w][d]; lo = fminf(lo, smin[w][d]); hi = fmaxf(hi, smax[w][d]); }
+                st.mean[d] = (float)(a / (double)(e - s));
+                st.bmin[d] = lo; st.bmax[d] = hi;
+            }
+            out[c] = st;
+        }
+    }
+}
+
+// ---- K8: the reference's getCentroid (MOT.cpp:708-822) ----------------------------------------------------------
+// Step 1 (farthest pair, O(n^2)) is spread over `slabs` CTAs per cluster (rows i = slab, slab+slabs, ...); each
+// writes its best candidate; step 2/3 (farthest point from the XY line, circumcentre) reduce them per cluster.
+// The reference's scan keeps the FIRST pair, in (i, j) lexicographic order, whose float distance is strictly
+// the largest; candidates are therefore compared as (dist desc, i asc, j asc).
+struct PairCand {
+    float dist;
+    int i, j;
+};
+__device__ __forceinline__ bool cand_better(const PairCand& a, const PairCand& b) {  // a beats b
+    if (a.dist != b.dist) return a.dist > b.dist;
+    if (a.i != b.i) return a.i < b.i;
+    return a.j < b.j;
+}
+__device__ __forceinline__ float ref_euc_dist(const float4& a, const float4& b) {  // MOT.cpp:1025-1028, fp64 then float
+    const double dx = __dsub_rn((double)a.x, (double)b.x), dy = __dsub_rn((double)a.y, (double)b.y), dz = __dsub_rn((double)a.z, (double)b.z);
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return __double2float_rn(__dsqrt_rn(s));
+}
+
+constexpr int FP_THREADS = 256;
+constexpr int FP_SMEM_POINTS = 2048;
+__global__ void __launch_bounds__(FP_THREADS) k_farthest_pair(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
+                                                               const uint32_t* __restrict__ indices, int K, int slabs,
+                                                               PairCand* __restrict__ cands /* [K][slabs] */) {
+    __shared__ float4 sp[FP_SMEM_POINTS];
+    __shared__ PairCand sbest[FP_THREADS / 32];
+    const int c = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+    if (c >= K) return;
+    const int s = cl_offsets[c], n = cl_offsets[c + 1] - s;
+    const bool staged = n <= FP_SMEM_POINTS;
+    if (staged) {
+        for (int t = threadIdx.x; t < n; t += FP_THREADS) sp[t] = pts[indices[s + t]];
+        __syncthreads();
+    }
+    PairCand best;
+    best.dist = -1.0f; best.i = 0x7fffffff; best.j = 0x7fffffff;
+    // rows are dealt to (slab, warp) round-robin; the lanes of a warp sweep j
+    const int row_stride = slabs * (FP_THREADS / 32);
+    for (int i = slab * (FP_THREADS / 32) + warp_id(); i < n - 1; i += row_stride) {
+        const float4 pi = staged ? sp[i] : pts[indices[s + i]];
+        for (int j = i + 1 + lane_id(); j < n; j += 32) {
+            const float4 pj = staged ? sp[j] : pts[indices[s + j]];
+            const float d = ref_euc_dist(pi, pj);
+            if (d > best.dist) { best.dist = d; best.i = i; best.j = j; }  // j ascending within a lane: strict > keeps the first
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        PairCand other;
+        other.dist = __shfl_xor_sync(kFull, best.dist, o);
+        other.i = __shfl_xor_sync(kFull, best.i, o);
+        other.j = __shfl_xor_sync(kFull, best.j, o);
+        if (cand_better(other, best)) best = other;
+    }
+    if (lane_id() == 0) sbest[warp_id()] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < FP_THREADS / 32; ++w)
+            if (cand_better(sbest[w], best)) best = sbest[w];
+        cands[(size_t)c * slabs + slab] = best;
+    }
+}
+
+constexpr int CC_THREADS = 128;
+__global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
+                                                              const uint32_t* __restrict__ indices, int K, int slabs,
+                                                              const PairCand* __restrict__ cands, float intensity, float4* __restrict__ out) {
+    __shared__ float sdist[CC_THREADS / 32];
+    __shared__ int sk[CC_THREADS / 32];
+    for (int c = blockIdx.x; c < K; c += gridDim.x) {
+        const int s = cl_offsets[c], n = cl_offsets[c + 1] - s;
+        PairCand best;
+        best.dist = -1.0f; best.i = 0x7fffffff; best.j = 0x7fffffff;
+        for (int t = 0; t < slabs; ++t) {
+            const PairCand o = cands[(size_t)c * slabs + t];
+            if (cand_better(o, best)) best = o;
+        }
+        // Pi, Pj, Vij as the reference leaves them after the pair loop (zero if the cluster has < 2 points)
+        double Pi[3] = {0, 0, 0}, Pj[3] = {0, 0, 0}, V0 = 0, V1 = 0, V2 = 0;
+        if (best.dist >= 0.0f) {
+            const float4 a = pts[indices[s + best.i]], b = pts[indices[s + best.j]];
+            Pi[0] = a.x; Pi[1] = a.y; Pi[2] = a.z;
+            Pj[0] = b.x; Pj[1] = b.y; Pj[2] = b.z;
+            V0 = __ddiv_rn(__dsub_rn(Pj[1], Pi[1]), __dsub_rn(Pj[0], Pi[0]));  // MOT.cpp:753
+            V1 = -1.0;
+            V2 = __dadd_rn(__dmul_rn(V0, -Pi[0]), Pi[1]);                      // MOT.cpp:755
+        }
+        // step 2: first k with strictly largest float line distance, skipping points equal to Pi / Pj.
+        // (the reference only updates dist_max when the point is accepted, so skipped points do not raise the bar)
+        const double denom = __dsqrt_rn(__dadd_rn(__dmul_rn(V0, V0), __dmul_rn(V1, V1)));
+        float bd = -1.0f;
+        int bk = 0x7fffffff;
+        for (int k = threadIdx.x; k < n; k += CC_THREADS) {
+            const float4 p = pts[indices[s + k]];
+            const double px = p.x, py = p.y, pz = p.z;
+            const double num = fabs(__dadd_rn(__dadd_rn(__dmul_rn(V0, px), __dmul_rn(V1, py)), V2));
+            const float d = __double2float_rn(__ddiv_rn(num, denom));
+            const bool eqi = px == Pi[0] && py == Pi[1] && pz == Pi[2];
+            const bool eqj = px == Pj[0] && py == Pj[1] && pz == Pj[2];
+            if (d > bd && !eqi && !eqj) { bd = d; bk = k; }  // NaN distances never satisfy >, as in the reference
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(kFull, bd, o);
+            const int ok = __shfl_xor_sync(kFull, bk, o);
+            if (od > bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+        }
+        __syncthreads();
+        if (lane_id() == 0) { sdist[warp_id()] = bd; sk[warp_id()] = bk; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < CC_THREADS / 32; ++w)
+                if (sdist[w] > bd || (sdist[w] == bd && sk[w] < bk)) { bd = sdist[w]; bk = sk[w]; }
+            double Pk[3] = {0, 0, 0};  // UB policy: zero-initialised
+            if (bk != 0x7fffffff && bd >= 0.0f) {
+                const float4 p = pts[indices[s + bk]];
+                Pk[0] = p.x; Pk[1] = p.y; Pk[2] = p.z;
+            }
+            // step 3, MOT.cpp:787-809: float A..G from double expressions, float final arithmetic, no FMA
+            const float A = __double2float_rn(__dsub_rn(Pj[0], Pi[0]));
+            const float B = __double2float_rn(__dsub_rn(Pj[1], Pi[1]));
+            const float C = __double2float_rn(__dsub_rn(Pk[0], Pi[0]));
+            const float D = __double2float_rn(__dsub_rn(Pk[1], Pi[1]));
+            const float E = __double2float_rn(__dadd_rn(__dmul_rn((double)A, __dadd_rn(Pi[0], Pj[0])), __dmul_rn((double)B, __dadd_rn(Pi[1], Pj[1]))));
+            const float F = __double2float_rn(__dadd_rn(__dmul_rn((double)C, __dadd_rn(Pi[0], Pk[0])), __dmul_rn((double)D, __dadd_rn(Pi[1], Pk[1]))));
+            const float G = __double2float_rn(__dmul_rn(2.0, __dsub_rn(__dmul_rn((double)A, __dsub_rn(Pk[1], Pj[1])), __dmul_rn((double)B, __dsub_rn(Pk[0], Pj[0])))));
+            float4 o;
+            if (G == 0.0f) { o.x = __double2float_rn(Pi[0]); o.y = __double2float_rn(Pi[1]); }
+            else {
+                o.x = __fdiv_rn(__fsub_rn(__fmul_rn(D, E), __fmul_rn(B, F)), G);
+                o.y = __fdiv_rn(__fsub_rn(__fmul_rn(A, F), __fmul_rn(C, E)), G);
+            }
+            o.z = 0.0f;
+            o.w = intensity;
+            out[c] = o;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace mot

@@ -1,0 +1,85 @@
+// ihgp.cuh -- K9: batched Infinite-Horizon GP track filter, one warp per track.
+//
+// Replaces the per-track loop of ObstacleTrack::callIHGP (reference MOT.cpp:621-662): LPF_pos
+// (MOT.cpp:824-833) and IHGP_fixed_vel (MOT.cpp:871-920), i.e. InfiniteHorizonGP::init_step + (L-1) x update
+// + getEft (IHGP.cpp:108-196) for the x and the y axis, then the +-1.5 m/s clamp (MOT.cpp:649-654).
+// The stationary matrices (A, AKHA, K, G) are per-axis constants computed once on the host
+// (mot_ihgp_configure; IHGP.cpp:12-37, 168-170) and passed by value.  The likelihood / gradient
+// recursion of update() (IHGP.cpp:138-154) feeds nothing the tracker reads and is not computed.
+//
+// Warp layout: all 32 lanes stage the ring and the finite-difference velocities in shared memory; lane 0 (x)
+// and lane 1 (y) then run the 2x2 recursions in the reference's own operation order in fp64 -- the arithmetic
+// is ~10^3 flops per track and latency bound, so bit-faithful sequential order costs nothing measurable.
+#pragma once
+#include "common.cuh"
+
+namespace mot {
+
+struct IhgpAxis {
+    double A[4], AKHA[4], K[2], G[4];
+};
+
+constexpr int IHGP_WARPS = 4;
+
+__global__ void __launch_bounds__(IHGP_WARPS * 32) k_ihgp_step(const float4* __restrict__ rings, int T, int L, float dt_gp, float lpf_tau,
+                                                                IhgpAxis ax, IhgpAxis ay, double* __restrict__ m_state,
+                                                                float4* __restrict__ pos_vel) {
+    extern __shared__ double ihgp_smem[];
+    const int n = L - 1;
+    double* wbase = ihgp_smem + (size_t)warp_id() * n * 6;
+    const int lane = lane_id();
+    for (int t = blockIdx.x * IHGP_WARPS + warp_id(); t < T; t += gridDim.x * IHGP_WARPS) {
+        const float4* c = rings + (size_t)t * L;
+        for (int k = lane; k < n; k += 32) {
+            const float4 c0 = c[k], c1 = c[k + 1];
+            wbase[k] = (double)__fdiv_rn(__fsub_rn(c1.x, c0.x), dt_gp);      // MOT.cpp:889 (float arithmetic)
+            wbase[n + k] = (double)__fdiv_rn(__fsub_rn(c1.y, c0.y), dt_gp);  // MOT.cpp:893
+        }
+        __syncwarp();
+        float vel = 0.0f;
+        if (lane < 2) {
+            const IhgpAxis& q = lane == 0 ? ax : ay;
+            const double* v = wbase + lane * n;
+            double* mf0 = wbase + 2 * n + lane * 2 * n;
+            double* mf1 = mf0 + n;
+            double mean = 0.0;  // uninitialised in the reference (MOT.cpp:879-880); policy: 0
+            for (int k = 0; k < n; ++k) mean = __dadd_rn(mean, v[k]);
+            mean = __ddiv_rn(mean, (double)n);
+            double m0 = m_state[(size_t)t * 4 + 2 * lane], m1 = m_state[(size_t)t * 4 + 2 * lane + 1];
+            for (int k = 0; k < n; ++k) {  // update(): m = AKHA*m + K*y  (IHGP.cpp:157)
+                const double y = __dsub_rn(v[k], mean);
+                const double n0 = __dadd_rn(__dadd_rn(__dmul_rn(q.AKHA[0], m0), __dmul_rn(q.AKHA[1], m1)), __dmul_rn(q.K[0], y));
+                const double n1 = __dadd_rn(__dadd_rn(__dmul_rn(q.AKHA[2], m0), __dmul_rn(q.AKHA[3], m1)), __dmul_rn(q.K[1], y));
+                m0 = n0; m1 = n1;
+                mf0[k] = m0; mf1[k] = m1;
+            }
+            const double eft_last = m0;  // H*MF.back(), H = [1 0]
+            for (int k = n - 2; k >= 0; --k) {  // getEft(): m = MF[k] + G*(m - A*MF[k])  (IHGP.cpp:185-189)
+                const double f0 = mf0[k], f1 = mf1[k];
+                const double r0 = __dsub_rn(m0, __dadd_rn(__dmul_rn(q.A[0], f0), __dmul_rn(q.A[1], f1)));
+                const double r1 = __dsub_rn(m1, __dadd_rn(__dmul_rn(q.A[2], f0), __dmul_rn(q.A[3], f1)));
+                m0 = __dadd_rn(f0, __dadd_rn(__dmul_rn(q.G[0], r0), __dmul_rn(q.G[1], r1)));
+                m1 = __dadd_rn(f1, __dadd_rn(__dmul_rn(q.G[2], r0), __dmul_rn(q.G[3], r1)));
+            }
+            m_state[(size_t)t * 4 + 2 * lane] = m0;      // smoothed state at k = 0 is the next frame's carry-in
+            m_state[(size_t)t * 4 + 2 * lane + 1] = m1;
+            vel = __double2float_rn(__dadd_rn(eft_last, mean));  // MOT.cpp:914-915
+            vel = vel > 1.5f ? 1.5f : (vel < -1.5f ? -1.5f : vel);  // MOT.cpp:649-654 (NaN passes through, as in the reference)
+        }
+        const float vy = __shfl_sync(kFull, vel, 1);
+        if (lane == 0) {
+            const float4 a = c[L - 2], b = c[L - 1];
+            const float wa = __fdiv_rn(lpf_tau, __fadd_rn(lpf_tau, dt_gp)), wb = __fdiv_rn(dt_gp, __fadd_rn(lpf_tau, dt_gp));
+            float4 pos, v4;
+            pos.x = __fadd_rn(__fmul_rn(wa, a.x), __fmul_rn(wb, b.x));  // MOT.cpp:827
+            pos.y = __fadd_rn(__fmul_rn(wa, a.y), __fmul_rn(wb, b.y));  // MOT.cpp:828
+            pos.z = 0.0f; pos.w = b.w;
+            v4.x = vel; v4.y = vy; v4.z = 0.0f; v4.w = b.w;
+            pos_vel[(size_t)t * 2] = pos;
+            pos_vel[(size_t)t * 2 + 1] = v4;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace mot

@@ -1,0 +1,911 @@
+// mot_b200.cu -- host side of libmot_b200.so: the C ABI declared in include/mot_b200.h and the per-frame
+// launch sequence.  C++ host code calling hand-written sm_100a kernels; no PyTorch, no CPU fallback.
+//
+// Frame pipeline (one CUDA stream per handle, two host round trips of 32 bytes each):
+//   K0  k_rs_count / k_rs_compact     removeStatic: bit lookup + stable compaction (+ bbox of kept points)
+//   --  S1: read M and the bounding box (sizes the grid: key width, radix passes, hash table)
+//   K1  k_cell_keys                   fp64 cell coordinates -> voxel key
+//   K2  k_rs_hist/scan/scatter        LSD radix sort of (key, index), ceil(bits/10) passes
+//   K3  k_cells_count / k_cells_write reorder to sorted SoA, fine/coarse cell tables, coarse-cell hash
+//   K4  k_uf_pairs<1>, <2>            27-coarse-cell witness search + atomicMin hooking (rings 1 and 2)
+//   K5  k_uf_flatten                  pointer jumping
+//   K6  k_comp_accumulate/k_kept_list component sizes, [min,max] filter
+//   --  S2: read K (sizes the cluster sort and the CSR partition)
+//       k_clusters_small | radix64    order clusters (size desc, min index asc), CSR offsets
+//       k_point_rank + radix32        stable partition of point indices by cluster rank = CSR indices
+//   K7  k_cluster_stats               segmented reduction: count / mean / bbox
+//   K8  k_farthest_pair/k_circumcentre  the reference's getCentroid
+//   K9  k_ihgp_step                   batched track filter (separate entry point)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mot_b200.h"
+#include "cluster_table.cuh"
+#include "common.cuh"
+#include "grid_uf.cuh"
+#include "ihgp.cuh"
+#include "radix_sort.cuh"
+#include "remove_static.cuh"
+
+using namespace mot;
+
+static_assert(sizeof(mot_cluster_stat) == sizeof(ClusterStat), "stat layout");
+static_assert(sizeof(mot_cluster_stat) == 40, "stat layout");
+
+struct mot_handle {
+    int device = 0;
+    size_t max_points = 0, max_tracks = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int num_sms = 148;
+
+    // launch parameters (reference defaults, MOT.cpp:90-92)
+    float tol = 0.15f;
+    int min_size = 5, max_size = 200;
+
+    // map
+    bool have_map = false;
+    MapParams mp{};
+    uint32_t* d_bits = nullptr;
+    size_t bits_capacity_words = 0;
+
+    // frame workspace
+    float4 *d_in = nullptr, *d_pts = nullptr, *d_spts = nullptr;
+    void* d_keys[2] = {nullptr, nullptr};  // 8 bytes per point each (u32 or u64 keys)
+    uint32_t* d_vals[2] = {nullptr, nullptr};
+    int *d_fc_start = nullptr, *d_cc_first = nullptr, *d_pcell = nullptr, *d_parent = nullptr, *d_root = nullptr;
+    int *d_csize = nullptr, *d_cmin = nullptr, *d_crank = nullptr, *d_labels = nullptr;
+    void* d_hkeys = nullptr;
+    int* d_hvals = nullptr;
+    size_t hash_capacity = 0;
+    RadixWorkspace rws;
+    int* d_blk = nullptr;     // 4 * 1024 per-block counters
+    int* d_counts = nullptr;  // CNT_N ints
+    int* d_bbox = nullptr;    // 8 ints
+    uint64_t* d_ckeys[2] = {nullptr, nullptr};
+    uint32_t* d_croots[2] = {nullptr, nullptr};
+    int* d_cl_offsets = nullptr;
+    int* d_frame_offsets = nullptr;
+    int* d_frame_cl_offsets = nullptr;
+    size_t frame_capacity = 0;
+    ClusterStat* d_stats = nullptr;
+    float4* d_centroids = nullptr;
+    PairCand* d_cands = nullptr;
+    size_t table_capacity = 0, cand_capacity = 0;
+    int* h_pinned = nullptr;  // 32 ints: counts + bbox readback
+
+    // IHGP
+    bool ihgp_ready = false;
+    double ihgp_consts[2][16];
+    IhgpAxis ihgp_axis[2];
+    double ihgp_dt = 0.1;
+    float ihgp_tau = 0.01f;
+    int ihgp_L = 10;
+    float4* d_rings = nullptr;
+    double* d_mstate = nullptr;
+    float4* d_posvel = nullptr;
+    size_t ring_capacity = 0;
+
+    // last result
+    bool have_result = false;
+    const float4* res_cloud = nullptr;  // the clustered cloud on the device (d_pts or the caller's pointer)
+    int res_M = 0, res_K = 0, res_total = 0, res_idx_buf = 0, res_frames = 1;
+    bool res_centroids = false;
+    int launches = 0;
+    cudaEvent_t ev[6] = {};
+    mot_timings tim{};
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                          \
+            return MOT_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(mot_handle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+int ceil_log2(long long v) {  // bits needed to represent values 0 .. v-1
+    int b = 0;
+    while ((1ll << b) < v) ++b;
+    return b;
+}
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) { return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T) + 256); }
+
+int ensure_tables(mot_handle* h, size_t K, size_t cands) {
+    if (K > h->table_capacity) {
+        size_t cap = K + K / 2 + 1024;
+        if (h->d_stats) cudaFree(h->d_stats);
+        if (h->d_centroids) cudaFree(h->d_centroids);
+        h->d_stats = nullptr; h->d_centroids = nullptr;
+        CK(dalloc(&h->d_stats, cap));
+        CK(dalloc(&h->d_centroids, cap));
+        h->table_capacity = cap;
+    }
+    if (cands > h->cand_capacity) {
+        size_t cap = cands + cands / 2 + 1024;
+        if (h->d_cands) cudaFree(h->d_cands);
+        h->d_cands = nullptr;
+        CK(dalloc(&h->d_cands, cap));
+        h->cand_capacity = cap;
+    }
+    return MOT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// removeStatic stage: d_src[n] -> d_pts[M], M and bbox left in device memory (read at S1 by cluster_core)
+// ------------------------------------------------------------------------------------------------------------
+int enqueue_remove_static(mot_handle* h, const float4* d_src, int n) {
+    const Chunking ck = make_chunking(n, RSK_THREADS, RSK_MAX_GRID);
+    const size_t bitmap_bytes = (size_t)((h->mp.n_words * 4 + 15) & ~15);
+    const int use_smem = bitmap_bytes <= (size_t)RSK_SMEM_BITMAP_MAX ? 1 : 0;
+    const size_t smem = use_smem ? bitmap_bytes : 0;
+    k_rs_count<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_bbox);
+    k_rs_compact<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_pts,
+                                                           h->d_counts + CNT_M);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return MOT_OK;
+}
+
+int reset_frame_state(mot_handle* h) {
+    static const int bbox_init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
+    CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), h->stream));
+    CK(cudaMemcpyAsync(h->d_bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, h->stream));
+    h->launches = 0;
+    h->have_result = false;
+    return MOT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// clustering core.  cloud: device pointer to the (compacted) cloud.  m < 0: M is taken from d_counts[CNT_M]
+// (written by k_rs_compact) and the bbox was produced by k_rs_count; otherwise bbox is computed here.
+// ------------------------------------------------------------------------------------------------------------
+template <typename KT>
+int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCodec& g, int total_bits, int n_frames) {
+    cudaStream_t st = h->stream;
+    KT* keys[2] = {reinterpret_cast<KT*>(h->d_keys[0]), reinterpret_cast<KT*>(h->d_keys[1])};
+    k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]);
+    h->launches += 1;
+    const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, &h->launches);
+    const KT* skeys = keys[sb];
+    const uint32_t* svals = h->d_vals[sb];
+
+    // coarse-cell hash sized for at most min(M, #coarse cells) entries at load factor <= 0.5
+    long long coarse_cap = (long long)g.ncx * g.ncy * g.ncz * n_frames;
+    if (coarse_cap > M || coarse_cap <= 0) coarse_cap = M;
+    int hb = ceil_log2(2 * coarse_cap);
+    if (hb < 4) hb = 4;
+    const size_t hsize = (size_t)1 << hb;
+    if (hsize > h->hash_capacity) return fail(h, MOT_ERR_CAPACITY, "hash table capacity exceeded");
+    CK(cudaMemsetAsync(h->d_hkeys, 0xff, hsize * sizeof(KT), st));
+    const unsigned hmask = (unsigned)(hsize - 1);
+    const int hshift = 32 - hb;
+
+    const Chunking ck = make_chunking(M, CELL_THREADS, CELL_MAX_GRID);
+    k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk);
+    k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, M, ck.chunk, h->d_blk, h->d_fc_start, h->d_cc_first, h->d_pcell,
+                                                        h->d_parent, h->d_csize, h->d_cmin, h->d_crank, reinterpret_cast<KT*>(h->d_hkeys),
+                                                        h->d_hvals, hmask, hshift, h->d_counts);
+    h->launches += 2;
+    CK(cudaEventRecord(h->ev[2], st));
+
+    const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
+    int uf_grid = (M + UF_WARPS - 1) / UF_WARPS;
+    if (uf_grid > h->num_sms * 8) uf_grid = h->num_sms * 8;
+    int flat_grid = (M + 255) / 256;
+    if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
+    k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, reinterpret_cast<const KT*>(h->d_hkeys),
+                                                      h->d_hvals, hmask, hshift, h->d_counts, h->d_parent, g, r2);
+    k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts);
+    k_uf_pairs<KT, 2><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, reinterpret_cast<const KT*>(h->d_hkeys),
+                                                      h->d_hvals, hmask, hshift, h->d_counts, h->d_parent, g, r2);
+    k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts);
+    h->launches += 4;
+    CK(cudaEventRecord(h->ev[3], st));
+    CK(cudaGetLastError());
+    return MOT_OK;
+}
+
+int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, bool with_centroids, double stamp) {
+    cudaStream_t st = h->stream;
+    if (m_known >= 0) {
+        if (m_known > 0) {
+            int grid = (m_known + 255) / 256;
+            if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+            k_bbox<<<grid, 256, 0, st>>>(cloud, m_known, h->d_bbox);
+            h->launches += 1;
+        }
+    }
+    CK(cudaEventRecord(h->ev[1], st));
+    // ---- S1 ----
+    CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int M = m_known >= 0 ? m_known : h->h_pinned[8 + CNT_M];
+    h->res_cloud = cloud;
+    h->res_M = M;
+    h->res_K = 0;
+    h->res_total = 0;
+    h->res_frames = n_frames;
+    h->res_centroids = false;
+    if (h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
+    if (M == 0) {
+        for (int i = 1; i < 6; ++i) CK(cudaEventRecord(h->ev[i], st));
+        CK(cudaMemsetAsync(h->d_cl_offsets, 0, sizeof(int), st));
+        if (n_frames > 1) CK(cudaMemsetAsync(h->d_frame_cl_offsets, 0, (n_frames + 1) * sizeof(int), st));
+        h->have_result = true;
+        return MOT_OK;
+    }
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; ++d) {
+        mn[d] = ordered_to_float_bits(h->h_pinned[d]);
+        mx[d] = ordered_to_float_bits(h->h_pinned[3 + d]);
+    }
+    GridCodec g{};
+    const double hcell = (double)h->tol * (1.0 + 1.0 / 1024.0);  // coarse edge: tol * (1 + 2^-10)
+    const double e = hcell * 0.5;                               // fine (clique) edge
+    g.inv_e = 1.0 / e;
+    g.minx = mn[0]; g.miny = mn[1]; g.minz = mn[2];
+    long long nf[3];
+    for (int d = 0; d < 3; ++d) {
+        const double span = ((double)mx[d] - (double)mn[d]) * g.inv_e;
+        if (!(span < 1.0e9)) return fail(h, MOT_ERR_INVALID, "cloud extent / cluster_tolerance too large for the voxel grid");
+        nf[d] = (long long)std::floor(span) + 1;
+    }
+    g.nfx = (int)nf[0]; g.nfy = (int)nf[1]; g.nfz = (int)nf[2];
+    g.ncx = (g.nfx + 1) / 2; g.ncy = (g.nfy + 1) / 2; g.ncz = (g.nfz + 1) / 2;
+    g.bx = ceil_log2(g.ncx); g.by = ceil_log2(g.ncy); g.bz = ceil_log2(g.ncz);
+    g.n_frames = n_frames;
+    const int frame_bits = n_frames > 1 ? ceil_log2(n_frames) : 0;
+    const int total_bits = 3 + g.bx + g.by + g.bz + frame_bits;
+    if (total_bits > 63) return fail(h, MOT_ERR_INVALID, "voxel key does not fit in 64 bits");
+    int rc = total_bits <= 32 ? cluster_sorted_part<uint32_t>(h, cloud, M, g, total_bits, n_frames)
+                              : cluster_sorted_part<uint64_t>(h, cloud, M, g, total_bits, n_frames);
+    if (rc != MOT_OK) return rc;
+
+    // ---- K6: sizes, filter ----
+    ClusterKeyCodec kc{};
+    long long max_frame_len = M;  // single frame
+    kc.size_bits = ceil_log2((long long)std::min<long long>(h->max_size, M) + 1);
+    if (kc.size_bits < 1) kc.size_bits = 1;
+    kc.size_cap = (unsigned)((1ull << kc.size_bits) - 1);
+    kc.idx_bits = ceil_log2(max_frame_len + 1);
+    if (kc.idx_bits < 1) kc.idx_bits = 1;
+    const int ckey_bits = kc.size_bits + kc.idx_bits + frame_bits;
+    int cgrid = (M + 255) / 256;
+    if (cgrid > h->num_sms * 8) cgrid = h->num_sms * 8;
+    k_comp_accumulate<<<cgrid, 256, 0, st>>>(h->d_fc_start, h->d_root, h->d_csize, h->d_cmin, h->d_counts);
+    k_kept_list<<<cgrid, 256, 0, st>>>(h->d_root, h->d_csize, h->d_cmin, h->d_frame_offsets, n_frames, h->min_size, h->max_size, kc,
+                                        h->d_ckeys[0], h->d_croots[0], h->d_counts);
+    h->launches += 2;
+    // ---- S2 ----
+    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int K = h->h_pinned[8 + CNT_K];
+    const int total = h->h_pinned[8 + CNT_TOTAL];
+    h->res_K = K;
+    h->res_total = total;
+
+    const uint64_t* sorted_ckeys = nullptr;
+    if (K <= CL_SMALL_MAX) {
+        k_clusters_small<<<1, CL_SMALL_THREADS, CL_SMALL_SMEM, st>>>(h->d_ckeys[0], h->d_croots[0], K, kc, h->d_ckeys[1], h->d_crank, h->d_cl_offsets);
+        sorted_ckeys = h->d_ckeys[1];
+        h->launches += 1;
+    } else {
+        const int cb = radix_sort_pairs<uint64_t>(st, h->d_ckeys, h->d_croots, K, ckey_bits, false, h->rws, &h->launches);
+        const Chunking ck = make_chunking(K, CLF_THREADS, CLF_MAX_GRID);
+        k_clusters_count<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], K, ck.chunk, kc, h->d_blk);
+        k_clusters_finalize<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], h->d_croots[cb], K, ck.chunk, kc, h->d_blk, h->d_crank, h->d_cl_offsets);
+        sorted_ckeys = h->d_ckeys[cb];
+        h->launches += 2;
+    }
+    if (n_frames > 1) {
+        k_frame_cluster_offsets<<<(n_frames + 1 + 127) / 128, 128, 0, st>>>(sorted_ckeys, K, kc, n_frames, h->d_frame_cl_offsets);
+        h->launches += 1;
+    }
+    // ---- CSR emission: stable partition of 0..M-1 by cluster rank ----
+    uint32_t* pk[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
+    k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_pcell, h->d_root, h->d_crank, h->d_cmin, M, K, pk[0], h->d_labels);
+    h->launches += 1;
+    h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, &h->launches);
+    if (n_frames > 1 && total > 0) {
+        k_localize_indices<<<(total + 255) / 256, 256, 0, st>>>(h->d_vals[h->res_idx_buf], total, h->d_frame_offsets, n_frames);
+        h->launches += 1;
+    }
+    CK(cudaEventRecord(h->ev[4], st));
+
+    // ---- K7 / K8 ----
+    if (K > 0 && n_frames == 1) {
+        int slabs = 1;
+        if (with_centroids && K < 2000) {
+            slabs = (h->num_sms * 16 + K - 1) / K;
+            if (slabs > 64) slabs = 64;
+            if (slabs < 1) slabs = 1;
+        }
+        rc = ensure_tables(h, (size_t)K, with_centroids ? (size_t)K * slabs : 0);
+        if (rc != MOT_OK) return rc;
+        int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
+        k_cluster_stats<<<sgrid, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, h->d_stats);
+        h->launches += 1;
+        if (with_centroids) {
+            k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands);
+            k_circumcentre<<<sgrid, CC_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands, (float)stamp,
+                                                         h->d_centroids);
+            h->launches += 2;
+            h->res_centroids = true;
+        }
+    }
+    CK(cudaEventRecord(h->ev[5], st));
+    CK(cudaGetLastError());
+    h->have_result = true;
+    return MOT_OK;
+}
+
+int finish_timings(mot_handle* h) {
+    CK(cudaStreamSynchronize(h->stream));
+    float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
+    cudaEventElapsedTime(&t01, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&t12, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&t23, h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&t34, h->ev[3], h->ev[4]);
+    cudaEventElapsedTime(&t45, h->ev[4], h->ev[5]);
+    cudaEventElapsedTime(&t05, h->ev[0], h->ev[5]);
+    cudaGetLastError();  // a frame that ended early (M == 0 / error) may not have recorded every event
+    h->tim.remove_static_ms = t01;
+    h->tim.grid_build_ms = t12;
+    h->tim.union_find_ms = t23;
+    h->tim.cluster_table_ms = t34;
+    h->tim.reduce_ms = t45;
+    h->tim.total_ms = t05;
+    return MOT_OK;
+}
+
+int fetch_result(mot_handle* h, float* kept, size_t kept_cap, int32_t* offs, size_t offs_cap, int32_t* idx, size_t idx_cap,
+                 mot_cluster_stat* stats, float* cent, size_t table_cap) {
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    cudaStream_t st = h->stream;
+    if (kept) {
+        if (kept_cap < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "kept cloud buffer too small");
+        if (h->res_M) CK(cudaMemcpyAsync(kept, h->res_cloud, (size_t)h->res_M * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (offs) {
+        if (offs_cap < (size_t)h->res_K + 1) return fail(h, MOT_ERR_CAPACITY, "cluster_offsets buffer too small");
+        CK(cudaMemcpyAsync(offs, h->d_cl_offsets, ((size_t)h->res_K + 1) * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (idx) {
+        if (idx_cap < (size_t)h->res_total) return fail(h, MOT_ERR_CAPACITY, "point_indices buffer too small");
+        if (h->res_total) CK(cudaMemcpyAsync(idx, h->d_vals[h->res_idx_buf], (size_t)h->res_total * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (stats && h->res_K) {
+        if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "stats buffer too small");
+        if (h->res_frames != 1) return fail(h, MOT_ERR_STATE, "per-cluster tables are not produced in batch mode");
+        CK(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->res_K * sizeof(ClusterStat), cudaMemcpyDeviceToHost, st));
+    }
+    if (cent && h->res_K) {
+        if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "centroid buffer too small");
+        if (!h->res_centroids) return fail(h, MOT_ERR_STATE, "centroids were not computed for the last result");
+        CK(cudaMemcpyAsync(cent, h->d_centroids, (size_t)h->res_K * 16, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return MOT_OK;
+}
+
+int check_frame_args(mot_handle* h, const void* pts, size_t n) {
+    if (!h) return MOT_ERR_INVALID;
+    if (n > 0 && !pts) return fail(h, MOT_ERR_INVALID, "null point buffer");
+    if (n > h->max_points) return fail(h, MOT_ERR_CAPACITY, "frame larger than the handle's max_points");
+    if (n > 0x7ffffff0ull) return fail(h, MOT_ERR_CAPACITY, "frame too large");
+    return MOT_OK;
+}
+
+// compute centroids for an existing result that was produced without them
+int compute_centroids_late(mot_handle* h, double stamp) {
+    const int K = h->res_K;
+    if (K == 0) { h->res_centroids = true; return MOT_OK; }
+    int slabs = 1;
+    if (K < 2000) {
+        slabs = (h->num_sms * 16 + K - 1) / K;
+        if (slabs > 64) slabs = 64;
+    }
+    int rc = ensure_tables(h, (size_t)K, (size_t)K * slabs);
+    if (rc != MOT_OK) return rc;
+    const int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
+    k_farthest_pair<<<K * slabs, FP_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands);
+    k_circumcentre<<<sgrid, CC_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands, (float)stamp,
+                                                        h->d_centroids);
+    CK(cudaGetLastError());
+    h->res_centroids = true;
+    return MOT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+const char* mot_version(void) { return "mot_b200 0.1 (sm_100a)"; }
+
+int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** out) {
+    if (!out || max_points == 0 || max_points > 0x7ffffff0ull) return MOT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MOT_ERR_CUDA;
+    mot_handle* h = new mot_handle();
+    h->device = device;
+    h->max_points = max_points;
+    h->max_tracks = max_tracks;
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        h->num_sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        const size_t n = max_points;
+        CK(dalloc(&h->d_in, n));
+        CK(dalloc(&h->d_pts, n));
+        CK(dalloc(&h->d_spts, n));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMalloc(&h->d_keys[i], n * 8 + 256));
+            CK(dalloc(&h->d_vals[i], n));
+            CK(dalloc(&h->d_ckeys[i], n));
+            CK(dalloc(&h->d_croots[i], n));
+        }
+        CK(dalloc(&h->d_fc_start, n + 1));
+        CK(dalloc(&h->d_cc_first, n + 1));
+        CK(dalloc(&h->d_pcell, n));
+        CK(dalloc(&h->d_parent, n));
+        CK(dalloc(&h->d_root, n));
+        CK(dalloc(&h->d_csize, n));
+        CK(dalloc(&h->d_cmin, n));
+        CK(dalloc(&h->d_crank, n));
+        CK(dalloc(&h->d_labels, n));
+        CK(dalloc(&h->d_cl_offsets, n + 1));
+        int hb = ceil_log2(2 * (long long)n);
+        if (hb < 4) hb = 4;
+        h->hash_capacity = (size_t)1 << hb;
+        CK(cudaMalloc(&h->d_hkeys, h->hash_capacity * 8));
+        CK(dalloc(&h->d_hvals, h->hash_capacity));
+        CK(dalloc(&h->rws.hist, rs_workspace_counters()));
+        CK(dalloc(&h->rws.prefix, rs_workspace_counters()));
+        CK(dalloc(&h->rws.tot, (size_t)1 << RS_MAX_BITS));
+        CK(dalloc(&h->d_blk, (size_t)4 * 1024));
+        CK(dalloc(&h->d_counts, (size_t)CNT_N));
+        CK(dalloc(&h->d_bbox, (size_t)8));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));
+        h->frame_capacity = 4096;
+        CK(dalloc(&h->d_frame_offsets, h->frame_capacity + 2));
+        CK(dalloc(&h->d_frame_cl_offsets, h->frame_capacity + 2));
+        CK(cudaMemset(h->d_frame_offsets, 0, (h->frame_capacity + 2) * sizeof(int)));
+        for (auto& e : h->ev) CK(cudaEventCreate(&e));
+        CK(rs_configure<uint32_t>());
+        CK(rs_configure<uint64_t>());
+        CK(cudaFuncSetAttribute(k_clusters_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMALL_SMEM));
+        CK(cudaFuncSetAttribute(k_rs_count, cudaFuncAttributeMaxDynamicSharedMemorySize, RSK_SMEM_BITMAP_MAX));
+        CK(cudaFuncSetAttribute(k_rs_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, RSK_SMEM_BITMAP_MAX));
+        if (max_tracks > 0) {
+            CK(dalloc(&h->d_mstate, max_tracks * 4));
+            CK(dalloc(&h->d_posvel, max_tracks * 2));
+        }
+        return MOT_OK;
+    };
+    const int rc = body();
+    if (rc != MOT_OK) {
+        fprintf(stderr, "mot_create: %s\n", h->err.c_str());
+        mot_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MOT_OK;
+}
+
+int mot_destroy(mot_handle* h) {
+    if (!h) return MOT_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {h->d_in, h->d_pts, h->d_spts, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_ckeys[0], h->d_ckeys[1],
+                    h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_pcell, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
+                    h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->d_blk,
+                    h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_centroids, h->d_cands, h->d_bits,
+                    h->d_rings, h->d_mstate, h->d_posvel};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MOT_OK;
+}
+
+const char* mot_last_error(mot_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int mot_set_map(mot_handle* h, const int8_t* occ, int width, int height, float resolution, double origin_x, double origin_y,
+                const double quat_xyzw[4], int static_tolerance) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!occ || !quat_xyzw || width <= 0 || height <= 0 || !(resolution > 0.0f) || (long long)width * height > 0x7fffffffll)
+        return fail(h, MOT_ERR_INVALID, "bad map arguments");
+    CK(cudaSetDevice(h->device));
+    if (static_tolerance > 4) static_tolerance = 4; else if (static_tolerance < 0) static_tolerance = 0;  // MOT.cpp:95-96
+    const size_t cells = (size_t)width * height;
+    const size_t words = (cells + 31) / 32;
+    const size_t padded_words = (words + 3) & ~(size_t)3;  // 16-byte multiple for the TMA bulk copy
+    if (padded_words > h->bits_capacity_words) {
+        if (h->d_bits) cudaFree(h->d_bits);
+        h->d_bits = nullptr;
+        CK(dalloc(&h->d_bits, padded_words));
+        h->bits_capacity_words = padded_words;
+    }
+    int8_t* d_occ = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&d_occ), cells));
+    cudaError_t e = cudaMemcpyAsync(d_occ, occ, cells, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->d_bits, 0, padded_words * 4, h->stream);
+    if (e == cudaSuccess) {
+        k_build_blocked_bitmap<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(d_occ, width, height, static_tolerance, h->d_bits);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_occ);
+    if (e != cudaSuccess) { h->err = std::string("mot_set_map: ") + cudaGetErrorString(e); return MOT_ERR_CUDA; }
+    // yaw exactly as quaternion2eularYaw (MOT.cpp:1013-1023): double atan2 returned through a float; then the
+    // float overloads of cos/sin the reference's `cos(-theta)` resolves to (MOT.cpp:677-678).
+    const double siny_cosp = 2 * (quat_xyzw[3] * quat_xyzw[2] + quat_xyzw[0] * quat_xyzw[1]);
+    const double cosy_cosp = 1 - 2 * (quat_xyzw[1] * quat_xyzw[1] + quat_xyzw[2] * quat_xyzw[2]);
+    const float theta = (float)std::atan2(siny_cosp, cosy_cosp);
+    h->mp.cs = std::cos(-theta);
+    h->mp.sn = std::sin(-theta);
+    h->mp.origin_x = origin_x;
+    h->mp.origin_y = origin_y;
+    h->mp.resolution = resolution;
+    h->mp.width = width;
+    h->mp.height = height;
+    h->mp.n_words = (int)words;
+    h->have_map = true;
+    return MOT_OK;
+}
+
+int mot_set_cluster_params(mot_handle* h, float cluster_tolerance, int min_cluster_size, int max_cluster_size) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!(cluster_tolerance > 0.0f) || !std::isfinite(cluster_tolerance)) return fail(h, MOT_ERR_INVALID, "cluster_tolerance must be > 0");
+    if (min_cluster_size < 1) min_cluster_size = 1;  // PCL: a component always has >= 1 point
+    h->tol = cluster_tolerance;
+    h->min_size = min_cluster_size;
+    h->max_size = max_cluster_size;
+    return MOT_OK;
+}
+
+int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xyz16, size_t out_capacity, size_t* m) {
+    int rc = check_frame_args(h, xyz16, n);
+    if (rc != MOT_OK) return rc;
+    if (!h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
+    if (!m) return fail(h, MOT_ERR_INVALID, "null output");
+    CK(cudaSetDevice(h->device));
+    *m = 0;
+    if (n == 0) return MOT_OK;
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = enqueue_remove_static(h, h->d_in, (int)n);
+    if (rc != MOT_OK) return rc;
+    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t M = (size_t)h->h_pinned[8 + CNT_M];
+    *m = M;
+    if (out_xyz16) {
+        if (out_capacity < M) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
+        if (M) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, M * 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return MOT_OK;
+}
+
+int mot_cluster(mot_handle* h, const float* xyz16, size_t m, int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices,
+                size_t indices_capacity, int32_t* n_clusters) {
+    int rc = check_frame_args(h, xyz16, m);
+    if (rc != MOT_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (m) CK(cudaMemcpyAsync(h->d_pts, xyz16, m * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = cluster_core(h, h->d_pts, (int)m, 1, false, 0.0);
+    if (rc != MOT_OK) return rc;
+    if (n_clusters) *n_clusters = h->res_K;
+    rc = fetch_result(h, nullptr, 0, cluster_offsets, offsets_capacity, point_indices, indices_capacity, nullptr, nullptr, 0);
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+int mot_cluster_stats(mot_handle* h, mot_cluster_stat* stats, size_t capacity) {
+    if (!h || !stats) return h ? fail(h, MOT_ERR_INVALID, "null output") : MOT_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    return fetch_result(h, nullptr, 0, nullptr, 0, nullptr, 0, stats, nullptr, capacity);
+}
+
+int mot_get_centroid(mot_handle* h, double stamp_minus_time_init, float* out_xyzi, size_t capacity) {
+    if (!h || !out_xyzi) return h ? fail(h, MOT_ERR_INVALID, "null output") : MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    if (h->res_frames != 1) return fail(h, MOT_ERR_STATE, "centroids are not produced in batch mode");
+    CK(cudaSetDevice(h->device));
+    int rc = compute_centroids_late(h, stamp_minus_time_init);
+    if (rc != MOT_OK) return rc;
+    return fetch_result(h, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, out_xyzi, capacity);
+}
+
+int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remove_static, int with_centroids, double stamp) {
+    int rc = check_frame_args(h, d_xyz16, n);
+    if (rc != MOT_OK) return rc;
+    if (do_remove_static && !h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
+    CK(cudaSetDevice(h->device));
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    const float4* src = reinterpret_cast<const float4*>(d_xyz16);
+    if (do_remove_static && n > 0) {
+        rc = enqueue_remove_static(h, src, (int)n);
+        if (rc != MOT_OK) return rc;
+        rc = cluster_core(h, h->d_pts, -1, 1, with_centroids != 0, stamp);
+    } else {
+        rc = cluster_core(h, do_remove_static ? h->d_pts : src, (int)n, 1, with_centroids != 0, stamp);
+    }
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+int mot_frame(mot_handle* h, const float* xyz16, size_t n, double stamp, float* kept_xyz16, size_t kept_capacity, size_t* m,
+              int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters,
+              mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity) {
+    int rc = check_frame_args(h, xyz16, n);
+    if (rc != MOT_OK) return rc;
+    if (!h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
+    CK(cudaSetDevice(h->device));
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (n) {
+        CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
+        rc = enqueue_remove_static(h, h->d_in, (int)n);
+        if (rc != MOT_OK) return rc;
+        rc = cluster_core(h, h->d_pts, -1, 1, centroids_xyzi != nullptr, stamp);
+    } else {
+        rc = cluster_core(h, h->d_pts, 0, 1, centroids_xyzi != nullptr, stamp);
+    }
+    if (rc != MOT_OK) return rc;
+    if (m) *m = (size_t)h->res_M;
+    if (n_clusters) *n_clusters = h->res_K;
+    rc = fetch_result(h, kept_xyz16, kept_capacity, cluster_offsets, offsets_capacity, point_indices, indices_capacity, stats, centroids_xyzi,
+                      table_capacity);
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+int mot_result_counts(mot_handle* h, size_t* m, int32_t* n_clusters, size_t* n_indices) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    if (m) *m = (size_t)h->res_M;
+    if (n_clusters) *n_clusters = h->res_K;
+    if (n_indices) *n_indices = (size_t)h->res_total;
+    return MOT_OK;
+}
+
+int mot_result_device_ptrs(mot_handle* h, const float** d_kept, const int32_t** d_offsets, const int32_t** d_indices,
+                           const mot_cluster_stat** d_stats, const float** d_centroids) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    if (d_kept) *d_kept = reinterpret_cast<const float*>(h->res_cloud);
+    if (d_offsets) *d_offsets = h->d_cl_offsets;
+    if (d_indices) *d_indices = reinterpret_cast<const int32_t*>(h->d_vals[h->res_idx_buf]);
+    if (d_stats) *d_stats = reinterpret_cast<const mot_cluster_stat*>(h->d_stats);
+    if (d_centroids) *d_centroids = h->res_centroids ? reinterpret_cast<const float*>(h->d_centroids) : nullptr;
+    return MOT_OK;
+}
+
+int mot_result_fetch(mot_handle* h, float* kept_xyz16, size_t kept_capacity, int32_t* cluster_offsets, size_t offsets_capacity,
+                     int32_t* point_indices, size_t indices_capacity, mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity) {
+    if (!h) return MOT_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    return fetch_result(h, kept_xyz16, kept_capacity, cluster_offsets, offsets_capacity, point_indices, indices_capacity, stats, centroids_xyzi,
+                        table_capacity);
+}
+
+int mot_result_labels(mot_handle* h, int32_t* labels, size_t capacity) {
+    if (!h || !labels) return h ? fail(h, MOT_ERR_INVALID, "null output") : MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    if (capacity < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "labels buffer too small");
+    CK(cudaSetDevice(h->device));
+    if (h->res_M) CK(cudaMemcpyAsync(labels, h->d_labels, (size_t)h->res_M * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return MOT_OK;
+}
+
+int mot_last_timings(mot_handle* h, mot_timings* t) {
+    if (!h || !t) return MOT_ERR_INVALID;
+    *t = h->tim;
+    return MOT_OK;
+}
+
+int mot_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return MOT_ERR_INVALID;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? MOT_OK : MOT_ERR_CUDA;
+}
+int mot_host_unregister(void* ptr) {
+    if (!ptr) return MOT_ERR_INVALID;
+    return cudaHostUnregister(ptr) == cudaSuccess ? MOT_OK : MOT_ERR_CUDA;
+}
+
+// ---- batches -------------------------------------------------------------------------------------------------
+static int batch_setup(mot_handle* h, const int64_t* frame_offsets, int n_frames, size_t* total) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!frame_offsets || n_frames < 1) return fail(h, MOT_ERR_INVALID, "bad frame_offsets");
+    if ((size_t)n_frames > h->frame_capacity) return fail(h, MOT_ERR_CAPACITY, "too many frames in one batch (max 4096)");
+    if (frame_offsets[0] != 0) return fail(h, MOT_ERR_INVALID, "frame_offsets[0] must be 0");
+    std::vector<int> fo(n_frames + 1);
+    for (int f = 0; f <= n_frames; ++f) {
+        if (f && frame_offsets[f] < frame_offsets[f - 1]) return fail(h, MOT_ERR_INVALID, "frame_offsets must be non-decreasing");
+        if (frame_offsets[f] > (int64_t)h->max_points) return fail(h, MOT_ERR_CAPACITY, "batch larger than the handle's max_points");
+        fo[f] = (int)frame_offsets[f];
+    }
+    *total = (size_t)frame_offsets[n_frames];
+    CK(cudaSetDevice(h->device));
+    int rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_frame_offsets, fo.data(), fo.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // fo is a stack-owned pageable buffer
+    return MOT_OK;
+}
+
+int mot_cluster_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames) {
+    size_t total = 0;
+    int rc = batch_setup(h, frame_offsets, n_frames, &total);
+    if (rc != MOT_OK) return rc;
+    if (total > 0 && !d_xyz16) return fail(h, MOT_ERR_INVALID, "null point buffer");
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    rc = cluster_core(h, reinterpret_cast<const float4*>(d_xyz16), (int)total, n_frames, false, 0.0);
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+int mot_cluster_batch(mot_handle* h, const float* xyz16, const int64_t* frame_offsets, int n_frames, int32_t* frame_cluster_offsets,
+                      int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters) {
+    size_t total = 0;
+    int rc = batch_setup(h, frame_offsets, n_frames, &total);
+    if (rc != MOT_OK) return rc;
+    if (total > 0 && !xyz16) return fail(h, MOT_ERR_INVALID, "null point buffer");
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if (total) CK(cudaMemcpyAsync(h->d_pts, xyz16, total * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = cluster_core(h, h->d_pts, (int)total, n_frames, false, 0.0);
+    if (rc != MOT_OK) return rc;
+    if (n_clusters) *n_clusters = h->res_K;
+    if (frame_cluster_offsets) {
+        if (n_frames > 1) {
+            CK(cudaMemcpyAsync(frame_cluster_offsets, h->d_frame_cl_offsets, (size_t)(n_frames + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            frame_cluster_offsets[0] = 0;
+            frame_cluster_offsets[1] = h->res_K;
+        }
+    }
+    rc = fetch_result(h, nullptr, 0, cluster_offsets, offsets_capacity, point_indices, indices_capacity, nullptr, nullptr, 0);
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+// ---- IHGP ----------------------------------------------------------------------------------------------------
+namespace {
+struct M2 { double a, b, c, d; };
+M2 mul2(const M2& x, const M2& y) { return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; }
+M2 tr2(const M2& x) { return {x.a, x.c, x.b, x.d}; }
+M2 add2(const M2& x, const M2& y) { return {x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
+M2 sub2(const M2& x, const M2& y) { return {x.a - y.a, x.b - y.b, x.c - y.c, x.d - y.d}; }
+
+// Host-side constant setup: Matern-3/2 model (M32.cpp:15-24), discretisation, fixed-point DARE
+// (IHGP.cpp:213-252, <= 100 iterations, Frobenius 1e-10), stationary gain (IHGP.cpp:27-37) and the RTS smoother
+// gain (IHGP.cpp:168-170).  2x2 closed forms; no Eigen.
+void ihgp_setup_axis(double dt, const double hyp[3], double out[16]) {
+    const double sigma2 = hyp[0], magn = hyp[1], ell = hyp[2];
+    const double lam = std::sqrt(3.0) / ell;
+    const M2 Pinf{magn, 0, 0, magn * lam * lam};
+    const double R = sigma2;
+    const double ex = std::exp(-lam * dt);  // expm(F dt) for the double eigenvalue -lam
+    const M2 A{ex * (1 + lam * dt), ex * dt, ex * (-lam * lam * dt), ex * (1 - lam * dt)};
+    const M2 Q = sub2(Pinf, mul2(mul2(A, Pinf), tr2(A)));
+    M2 X{1, 0, 0, 1};
+    for (int n = 0; n < 100; ++n) {
+        const M2 Xp = X;
+        double k0 = 0, k1 = 0;
+        if (!(std::fabs(R) < 1e-15)) {
+            const double s = X.a + R;
+            const double v0 = X.a / s, v1 = X.c / s;
+            k0 = A.a * v0 + A.b * v1;
+            k1 = A.c * v0 + A.d * v1;
+        }
+        const M2 AKB{A.a - k0, A.b, A.c - k1, A.d};
+        const M2 KRK{k0 * R * k0, k0 * R * k1, k1 * R * k0, k1 * R * k1};
+        X = add2(add2(mul2(mul2(AKB, X), tr2(AKB)), KRK), Q);
+        const M2 dX = sub2(X, Xp);
+        if (std::sqrt(dX.a * dX.a + dX.b * dX.b + dX.c * dX.c + dX.d * dX.d) < 1e-10) break;
+    }
+    const M2 PP = X;
+    const double S = PP.a + R;
+    const double K0 = PP.a / S, K1 = PP.c / S;
+    const M2 PF = sub2(PP, M2{K0 * PP.a, K0 * PP.b, K1 * PP.a, K1 * PP.b});
+    const M2 AKHA = sub2(A, M2{K0 * A.a, K0 * A.b, K1 * A.a, K1 * A.b});
+    const M2 APF = mul2(A, PF);
+    const M2 PPs = add2(mul2(APF, tr2(A)), Q);
+    const double det = PPs.a * PPs.d - PPs.b * PPs.c;
+    const M2 inv{PPs.d / det, -PPs.b / det, -PPs.c / det, PPs.a / det};
+    const M2 G = tr2(mul2(inv, APF));
+    const double o[16] = {A.a, A.b, A.c, A.d, AKHA.a, AKHA.b, AKHA.c, AKHA.d, K0, K1, G.a, G.b, G.c, G.d, S, lam};
+    std::memcpy(out, o, sizeof(o));
+}
+}  // namespace
+
+int mot_ihgp_configure(mot_handle* h, double dt, float lpf_tau, const double hyp_x[3], const double hyp_y[3], int data_length) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!hyp_x || !hyp_y || !(dt > 0) || data_length < 3 || data_length > 1024) return fail(h, MOT_ERR_INVALID, "bad IHGP configuration");
+    for (int a = 0; a < 2; ++a) {
+        const double* hyp = a == 0 ? hyp_x : hyp_y;
+        if (!(hyp[0] > 0) || !(hyp[1] > 0) || !(hyp[2] > 0)) return fail(h, MOT_ERR_INVALID, "IHGP hyper-parameters must be positive");
+        ihgp_setup_axis((double)(float)dt, hyp, h->ihgp_consts[a]);  // dt_gp is a float in the reference (MOT.h:113) and widens at the ctor call
+        std::memcpy(h->ihgp_axis[a].A, h->ihgp_consts[a] + 0, 4 * sizeof(double));
+        std::memcpy(h->ihgp_axis[a].AKHA, h->ihgp_consts[a] + 4, 4 * sizeof(double));
+        std::memcpy(h->ihgp_axis[a].K, h->ihgp_consts[a] + 8, 2 * sizeof(double));
+        std::memcpy(h->ihgp_axis[a].G, h->ihgp_consts[a] + 10, 4 * sizeof(double));
+    }
+    h->ihgp_dt = dt;
+    h->ihgp_tau = lpf_tau;
+    h->ihgp_L = data_length;
+    h->ihgp_ready = true;
+    return MOT_OK;
+}
+
+int mot_ihgp_constants(mot_handle* h, int axis, double* consts16) {
+    if (!h || !consts16 || axis < 0 || axis > 1) return MOT_ERR_INVALID;
+    if (!h->ihgp_ready) return fail(h, MOT_ERR_STATE, "mot_ihgp_configure has not been called");
+    std::memcpy(consts16, h->ihgp_consts[axis], 16 * sizeof(double));
+    return MOT_OK;
+}
+
+int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_state, float* pos_vel) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!h->ihgp_ready) return fail(h, MOT_ERR_STATE, "mot_ihgp_configure has not been called");
+    if (n_tracks < 0 || (size_t)n_tracks > h->max_tracks) return fail(h, MOT_ERR_CAPACITY, "more tracks than the handle's max_tracks");
+    if (n_tracks == 0) return MOT_OK;
+    if (!rings || !m_state || !pos_vel) return fail(h, MOT_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->device));
+    const int L = h->ihgp_L;
+    const size_t ring_elems = (size_t)n_tracks * L;
+    if (ring_elems > h->ring_capacity) {
+        if (h->d_rings) cudaFree(h->d_rings);
+        h->d_rings = nullptr;
+        CK(dalloc(&h->d_rings, h->max_tracks * (size_t)L));
+        h->ring_capacity = h->max_tracks * (size_t)L;
+    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->d_rings, rings, ring_elems * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_mstate, m_state, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (n_tracks + IHGP_WARPS - 1) / IHGP_WARPS;
+    if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+    k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0], h->ihgp_axis[1],
+                                                     h->d_mstate, h->d_posvel);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return MOT_OK;
+}
+
+}  // extern "C"

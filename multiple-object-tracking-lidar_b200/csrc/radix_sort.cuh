@@ -1,0 +1,251 @@
+// radix_sort.cuh -- stable LSD radix sort of (key, u32 value) pairs, hand written for sm_100a.
+//
+// Used three times per frame: (1) points by voxel key (grid build), (2) clusters by
+// (size desc, min index asc), (3) the stable partition of point indices by cluster rank (CSR emission, K6).
+//
+// Per pass (digit width 1..10 bits, chosen by the host so that passes = ceil(key_bits / 10)):
+//   k_rs_hist     every block histograms the digit over its contiguous chunk          (reads keys)
+//   k_rs_scan     one warp per digit: exclusive prefix of that digit over the blocks  (R x G counters)
+//   k_rs_scatter  tile-wise stable ranking with warp match_any + per-warp counters, tile re-ordered in
+//                 shared memory so that global writes are coalesced runs              (reads + writes pairs)
+// No inter-block spin waits anywhere: a pass is three stream-ordered launches.
+#pragma once
+#include "common.cuh"
+
+namespace mot {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per tile
+constexpr int RS_MAX_BITS = 10;
+constexpr int RS_MAX_GRID = 592;  // 4 CTAs per SM x 148 SMs
+
+template <typename KT>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const KT* __restrict__ keys, int n, int chunk, int shift, int bits,
+                                                         unsigned* __restrict__ hist /* [R][G] */) {
+    extern __shared__ unsigned sh_hist[];
+    const int R = 1 << bits;
+    const unsigned mask = R - 1;
+    for (int d = threadIdx.x; d < R; d += RS_THREADS) sh_hist[d] = 0;
+    __syncthreads();
+    const int begin = blockIdx.x * chunk;
+    const int end = min(n, begin + chunk);
+    const int lane = lane_id();
+    for (int base = begin; base < end; base += RS_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool valid = i < end;
+        const unsigned d = valid ? (unsigned)((keys[i] >> shift) & mask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(kFull, d);
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh_hist[d], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < R; d += RS_THREADS) hist[(size_t)d * gridDim.x + blockIdx.x] = sh_hist[d];
+}
+
+// One warp per digit: prefix[d][b] = sum_{b' < b} hist[d][b'], tot[d] = sum_b hist[d][b].
+__global__ void __launch_bounds__(256) k_rs_scan(const unsigned* __restrict__ hist, unsigned* __restrict__ prefix,
+                                                  unsigned* __restrict__ tot, int R, int G) {
+    const int d = blockIdx.x * 8 + warp_id();
+    if (d >= R) return;
+    const int lane = lane_id();
+    const int per = (G + 31) / 32;
+    const int s = lane * per, e = min(G, s + per);
+    const unsigned* row = hist + (size_t)d * G;
+    unsigned* prow = prefix + (size_t)d * G;
+    int local = 0;
+    for (int i = s; i < e; ++i) local += (int)row[i];
+    const int incl = warp_inclusive_scan(local);
+    int run = incl - local;
+    for (int i = s; i < e; ++i) {
+        prow[i] = (unsigned)run;
+        run += (int)row[i];
+    }
+    if (lane == 31) tot[d] = (unsigned)incl;
+}
+
+constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes) {
+    return (size_t)(RS_WARPS + 2) * ((size_t)1 << bits) * 4 + 36 * 4 + (size_t)RS_TILE * 4 + (size_t)RS_TILE * key_bytes;
+}
+
+template <typename KT, bool IOTA>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                            KT* __restrict__ kout, uint32_t* __restrict__ vout, int n, int chunk,
+                                                            int shift, int bits, const unsigned* __restrict__ prefix,
+                                                            const unsigned* __restrict__ tot) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int R = 1 << bits;
+    const unsigned mask = R - 1;
+    unsigned* cnt = reinterpret_cast<unsigned*>(rs_smem);  // [RS_WARPS][R]
+    unsigned* tile_off = cnt + RS_WARPS * R;               // [R]
+    unsigned* gbase = tile_off + R;                        // [R]
+    int* scan_tmp = reinterpret_cast<int*>(gbase + R);     // [36]
+    uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 36);
+    KT* st_keys = reinterpret_cast<KT*>(st_vals + RS_TILE);
+
+    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const int G = gridDim.x, b = blockIdx.x;
+    const int per = (R + RS_THREADS - 1) / RS_THREADS;  // digits owned by a thread (<= 4)
+    const int d0 = tid * per;
+
+    // gbase[d] = (exclusive scan of tot over digits)[d] + prefix[d][b]
+    {
+        int local = 0;
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) local += (int)tot[d];
+        }
+        int total;
+        int run = block_exclusive_scan(local, scan_tmp, &total);
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) {
+                gbase[d] = (unsigned)run + prefix[(size_t)d * G + b];
+                run += (int)tot[d];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int begin = b * chunk;
+    const int end = min(n, begin + chunk);
+    for (int tile_begin = begin; tile_begin < end; tile_begin += RS_TILE) {
+        for (int i = tid; i < RS_WARPS * R; i += RS_THREADS) cnt[i] = 0;
+        __syncthreads();
+
+        KT key[RS_ITEMS];
+        uint32_t val[RS_ITEMS];
+        unsigned rank[RS_ITEMS];
+        const int seg = tile_begin + w * (32 * RS_ITEMS);
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int idx = seg + i * 32 + lane;
+            const bool valid = idx < end;
+            key[i] = valid ? kin[idx] : ~(KT)0;
+            if (IOTA) val[i] = (uint32_t)idx;
+            else val[i] = valid ? vin[idx] : 0u;
+        }
+        unsigned* wcnt = cnt + w * R;
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int idx = seg + i * 32 + lane;
+            const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;  // padding sorts last
+            const unsigned peers = __match_any_sync(kFull, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned old = 0;
+            if (lane == leader) {
+                old = wcnt[d];
+                wcnt[d] = old + (unsigned)__popc(peers);
+            }
+            old = __shfl_sync(kFull, old, leader);
+            rank[i] = old + (unsigned)__popc(peers & lanemask_lt());
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // per digit: exclusive prefix over the warps; tile_off[d] temporarily holds the tile's digit count
+        for (int d = tid; d < R; d += RS_THREADS) {
+            unsigned run = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ++ww) {
+                const unsigned t = cnt[ww * R + d];
+                cnt[ww * R + d] = run;
+                run += t;
+            }
+            tile_off[d] = run;
+        }
+        __syncthreads();
+        unsigned mycount[4] = {0, 0, 0, 0};
+        {
+            int local = 0;
+            for (int k = 0; k < per; ++k) {
+                const int d = d0 + k;
+                if (d < R) {
+                    mycount[k] = tile_off[d];
+                    local += (int)mycount[k];
+                }
+            }
+            int total;
+            int run = block_exclusive_scan(local, scan_tmp, &total);
+            for (int k = 0; k < per; ++k) {
+                const int d = d0 + k;
+                if (d < R) {
+                    tile_off[d] = (unsigned)run;
+                    run += (int)mycount[k];
+                }
+            }
+        }
+        __syncthreads();
+
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            const int idx = seg + i * 32 + lane;
+            const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;
+            const unsigned pos = tile_off[d] + wcnt[d] + rank[i];
+            st_keys[pos] = key[i];
+            st_vals[pos] = val[i];
+        }
+        __syncthreads();
+
+        const int tile_n = min(RS_TILE, end - tile_begin);
+        for (int j = tid; j < tile_n; j += RS_THREADS) {
+            const KT k = st_keys[j];
+            const unsigned d = (unsigned)((k >> shift) & mask);
+            const unsigned g = gbase[d] + ((unsigned)j - tile_off[d]);
+            kout[g] = k;
+            vout[g] = st_vals[j];
+        }
+        __syncthreads();
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) gbase[d] += mycount[k];
+        }
+        __syncthreads();
+    }
+}
+
+struct RadixWorkspace {
+    unsigned* hist = nullptr;    // [R_max][G_max]
+    unsigned* prefix = nullptr;  // [R_max][G_max]
+    unsigned* tot = nullptr;     // [R_max]
+};
+constexpr size_t rs_workspace_counters() { return (size_t)(1 << RS_MAX_BITS) * RS_MAX_GRID; }
+
+template <typename KT>
+inline cudaError_t rs_configure() {
+    cudaError_t e;
+    const int smem = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT));
+    e = cudaFuncSetAttribute(k_rs_scatter<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_rs_scatter<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+// Sorts n pairs by the low `key_bits` bits of the key.  Input in (k[0], v[0]) -- v[0] is ignored and treated
+// as 0..n-1 when iota_first.  Returns the index (0/1) of the buffer pair that holds the result.
+// *launches is incremented by the number of kernels enqueued.
+template <typename KT>
+inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, int key_bits, bool iota_first,
+                            const RadixWorkspace& ws, int* launches) {
+    if (key_bits < 1) key_bits = 1;
+    const int passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const int base = key_bits / passes, rem = key_bits % passes;
+    const Chunking ck = make_chunking(n, RS_TILE, RS_MAX_GRID);
+    int cur = 0, shift = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int bits = base + (p < rem ? 1 : 0);
+        const int R = 1 << bits;
+        k_rs_hist<KT><<<ck.grid, RS_THREADS, R * sizeof(unsigned), st>>>(k[cur], n, ck.chunk, shift, bits, ws.hist);
+        k_rs_scan<<<(R + 7) / 8, 256, 0, st>>>(ws.hist, ws.prefix, ws.tot, R, ck.grid);
+        const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT));
+        if (p == 0 && iota_first)
+            k_rs_scatter<KT, true><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+        else
+            k_rs_scatter<KT, false><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+        if (launches) *launches += 3;
+        cur ^= 1;
+        shift += bits;
+    }
+    return cur;
+}
+
+}  // namespace mot

@@ -1,0 +1,199 @@
+// remove_static.cuh -- K0: ObstacleTrack::removeStatic (reference MOT.cpp:664-706) as a bit lookup + stable
+// compaction, fused with the bounding-box reduction the voxel grid needs.
+//
+// The reference tests, per point, up to (2t+1)^2 cells of an Eigen::MatrixXd copy of the occupancy grid and
+// recomputes atan2/cos/sin of the (frame constant) map yaw.  Here the map is reduced ONCE (mot_set_map) to a
+// dilated bitmap  blocked[r][c] = OR over the window of (occ > 50 || occ == -1 || outside the map), so a point
+// costs one bit test; cos(-yaw), sin(-yaw) are computed on the host with the same libm float overloads the
+// reference calls and enter the kernel as constants.  The index arithmetic keeps the reference's exact fp32
+// operation sequence (no FMA) and its truncation toward zero.
+#pragma once
+#include "common.cuh"
+
+namespace mot {
+
+struct MapParams {
+    double origin_x, origin_y;
+    float cs, sn;        // cosf(-yaw), sinf(-yaw) from the host's libm
+    float resolution;
+    int width, height;
+    int n_words;         // bitmap words (row-major bit index r*width + c)
+};
+
+// blocked bit for every cell (MOT.cpp:681-702 folded over the window; out-of-map counts as unknown).
+__global__ void k_build_blocked_bitmap(const int8_t* __restrict__ occ, int W, int H, int t, uint32_t* __restrict__ bits) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * H) return;
+    const int r = idx / W, c = idx % W;
+    bool blocked = false;
+    for (int i = -t; i <= t && !blocked; ++i)
+        for (int j = -t; j <= t; ++j) {
+            const int rr = r + i, cc = c + j;
+            if (rr < 0 || cc < 0 || rr >= H || cc >= W) { blocked = true; break; }
+            const int v = occ[rr * W + cc];
+            if (v > 50 || v == -1) { blocked = true; break; }
+        }
+    if (blocked) atomicOr(&bits[idx >> 5], 1u << (idx & 31));
+}
+
+// keep decision for one point, bit-for-bit the reference's arithmetic (MOT.cpp:674-678).
+__device__ __forceinline__ bool rs_keep(const float4& p, const MapParams& mp, const uint32_t* bits) {
+    const float x_map = __double2float_rn(__dsub_rn((double)p.x, mp.origin_x));
+    const float y_map = __double2float_rn(__dsub_rn((double)p.y, mp.origin_y));
+    const float fc = __fdiv_rn(__fsub_rn(__fmul_rn(mp.cs, x_map), __fmul_rn(mp.sn, y_map)), mp.resolution);
+    const float fr = __fdiv_rn(__fadd_rn(__fmul_rn(mp.sn, x_map), __fmul_rn(mp.cs, y_map)), mp.resolution);
+    if (!(fabsf(fc) < 1073741824.0f) || !(fabsf(fr) < 1073741824.0f)) return false;  // NaN / huge -> drop
+    const int col = __float2int_rz(fc), row = __float2int_rz(fr);
+    if (row < 0 || col < 0 || row >= mp.height || col >= mp.width) return false;
+    const int idx = row * mp.width + col;
+    return ((bits[idx >> 5] >> (idx & 31)) & 1u) == 0u;
+}
+
+constexpr int RSK_THREADS = 256;
+constexpr int RSK_MAX_GRID = 592;
+constexpr int RSK_SMEM_BITMAP_MAX = 96 * 1024;  // bitmaps up to 96 KB are staged in shared memory with one TMA bulk copy
+
+struct FrameHeader;  // fwd (api)
+
+// Stages the bitmap into shared memory with a single TMA bulk copy (cp.async.bulk -> UBLKCP) when it fits;
+// returns the pointer the lookups should use.
+__device__ __forceinline__ const uint32_t* rs_stage_bitmap(const uint32_t* __restrict__ gbits, int n_words, bool use_smem,
+                                                           uint32_t* sbits, uint64_t* bar) {
+    if (!use_smem) return gbits;
+    const uint32_t bytes = (uint32_t)(((n_words * 4) + 15) & ~15);  // buffer is padded to 16 B on the host
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, bytes);
+        tma_load_1d(sbits, gbits, bytes, bar);
+    }
+    const bool ok = mbar_wait_bounded(bar, 0);
+    return ok ? sbits : gbits;  // a timed-out copy degrades to global lookups, never to a hang
+}
+
+// Pass 1: per-block kept count + bbox of kept points (ordered-int atomics) + non-finite flag.
+__global__ void __launch_bounds__(RSK_THREADS) k_rs_count(const float4* __restrict__ pts, int n, int chunk, MapParams mp,
+                                                           const uint32_t* __restrict__ gbits, int use_smem,
+                                                           int* __restrict__ block_counts, int* __restrict__ bbox /* 6 ordered ints + flag */) {
+    extern __shared__ __align__(16) uint32_t rs_sbits[];
+    __shared__ uint64_t bar;
+    __shared__ int red[33];
+    __shared__ int sbox[6];
+    const uint32_t* bits = rs_stage_bitmap(gbits, mp.n_words, use_smem != 0, rs_sbits, &bar);
+    if (threadIdx.x < 3) sbox[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) sbox[threadIdx.x] = (int)0x80000000;
+    __syncthreads();
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int cnt = 0;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (int i = begin + threadIdx.x; i < end; i += RSK_THREADS) {
+        const float4 p = ld_stream(pts + i);
+        if (rs_keep(p, mp, bits)) {
+            ++cnt;
+            if (!(fabsf(p.x) < INFINITY) || !(fabsf(p.y) < INFINITY) || !(fabsf(p.z) < INFINITY)) bad = true;
+            mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+            mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
+        }
+    if (lane_id() == 0 && cnt >= 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&sbox[d], float_to_ordered(mn[d]));
+            atomicMax(&sbox[3 + d], float_to_ordered(mx[d]));
+        }
+    }
+    if (__any_sync(kFull, bad) && lane_id() == 0) atomicOr(&bbox[6], 1);
+    cnt = warp_sum(cnt);
+    if (lane_id() == 0) red[warp_id()] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < RSK_THREADS / 32; ++w) s += red[w];
+        block_counts[blockIdx.x] = s;
+        if (s > 0) {
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(&bbox[d], sbox[d]);
+                atomicMax(&bbox[3 + d], sbox[3 + d]);
+            }
+        }
+    }
+}
+
+// Pass 2: stable compaction.  Block base = sum of the preceding blocks' counts; inside a tile the kept points
+// are ranked with ballots so the input order is preserved (MOT.cpp:694 appends in input order).
+__global__ void __launch_bounds__(RSK_THREADS) k_rs_compact(const float4* __restrict__ pts, int n, int chunk, MapParams mp,
+                                                             const uint32_t* __restrict__ gbits, int use_smem,
+                                                             const int* __restrict__ block_counts, float4* __restrict__ out,
+                                                             int* __restrict__ total_out) {
+    extern __shared__ __align__(16) uint32_t rs_sbits[];
+    __shared__ uint64_t bar;
+    __shared__ int red[36];
+    __shared__ int wbase[RSK_THREADS / 32 + 1];
+    const uint32_t* bits = rs_stage_bitmap(gbits, mp.n_words, use_smem != 0, rs_sbits, &bar);
+    int base = block_prefix_of(block_counts, blockIdx.x, red);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = base + block_counts[blockIdx.x];
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    const int lane = lane_id(), w = warp_id();
+    for (int tb = begin; tb < end; tb += RSK_THREADS) {
+        const int i = tb + threadIdx.x;
+        float4 p = make_float4(0, 0, 0, 0);
+        bool keep = false;
+        if (i < end) {
+            p = ld_stream(pts + i);
+            keep = rs_keep(p, mp, bits);
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        __syncthreads();
+        if (lane == 0) wbase[w] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < RSK_THREADS / 32; ++ww) {
+            const int c = wbase[ww];
+            if (ww < w) off += c;
+            tot += c;
+        }
+        if (keep) st_stream(out + base + off + __popc(bal & lanemask_lt()), p);
+        base += tot;
+    }
+}
+
+// Bounding box + finiteness of an already compacted cloud (mot_cluster without removeStatic).
+__global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, int n, int* __restrict__ bbox) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = ld_stream(pts + i);
+        if (!(fabsf(p.x) < INFINITY) || !(fabsf(p.y) < INFINITY) || !(fabsf(p.z) < INFINITY)) bad = true;
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
+        }
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&bbox[d], float_to_ordered(mn[d]));
+            atomicMax(&bbox[3 + d], float_to_ordered(mx[d]));
+        }
+    }
+    if (__any_sync(kFull, bad) && lane_id() == 0) atomicOr(&bbox[6], 1);
+}
+
+}  // namespace mot

@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same inputs.
+
+Bars: bit-exact for the removeStatic output, the cluster partition and the CSR arrays (integer / index work);
+rtol 1e-5 for centroids, bbox/mean and IHGP states (north_star's fp32 tolerance)."""
+import numpy as np
+import pytest
+
+from cases import kat_cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def trk(mot):
+    t = mot.Tracker(device=0, max_points=1 << 21, max_tracks=2048)
+    yield t
+    t.close()
+
+
+def check_extract(trk, oracle, pts, tol, mn, mx, brute=True):
+    trk.set_cluster_params(tol, mn, mx)
+    off, idx = trk.extract(pts)
+    if brute:
+        lab = oracle.labels_bruteforce(pts, tol)
+    else:
+        lab = oracle.labels_grid(pts, tol)
+    off_ref, idx_ref = oracle.csr_from_labels(lab, max(mn, 1), mx)
+    assert np.array_equal(trk.result_labels(), lab), "component labels differ"
+    assert np.array_equal(off, off_ref), "cluster offsets differ"
+    assert np.array_equal(idx, idx_ref), "point indices differ"
+    return off, idx
+
+
+@pytest.mark.parametrize("name", sorted(kat_cases().keys()))
+def test_kat(trk, oracle, name):
+    pts, tol, mn, mx, expect_k = kat_cases()[name]
+    off, idx = check_extract(trk, oracle, pts, tol, mn, mx)
+    if expect_k is not None:
+        assert len(off) - 1 == expect_k
+    # the reference path itself (KD-tree + BFS restatement) agrees as well
+    off_kd, idx_kd = oracle.cluster_kdtree(pts, tol, max(mn, 1), mx)
+    assert np.array_equal(off, off_kd) and np.array_equal(idx, idx_kd)
+
+
+def test_remove_static_sim01(trk, oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_01_occupancy.npz"))
+    occ, res, origin = g["occ"], float(g["resolution"]), g["origin"]
+    rng = np.random.default_rng(7)
+    H, W = occ.shape
+    n = 50000
+    xy = np.c_[rng.uniform(origin[0] - 0.5, origin[0] + W * res + 0.5, n), rng.uniform(origin[1] - 0.5, origin[1] + H * res + 0.5, n)]
+    pts = np.ones((n, 4), np.float32)
+    pts[:, :2] = xy
+    pts[:, 2] = rng.uniform(0, 2, n)
+    for t in (0, 2, 4):
+        for quat in ((0, 0, 0, 1), (0, 0, np.sin(0.35), np.cos(0.35))):
+            trk.set_map(occ, res, origin[:2], quat_xyzw=quat, static_tolarance=t)
+            kept = trk.remove_static(pts)
+            ref, keep = oracle.remove_static(pts, occ, res, origin[:2], quat_xyzw=quat, static_tolerance=t)
+            assert 0 < len(ref) < n
+            assert np.array_equal(kept, ref)
+
+
+def test_remove_static_large_map_and_edges(trk, oracle, synth):
+    # a bitmap too large for shared memory (global lookups) and points outside / on the border of the map
+    occ = np.zeros((1200, 1100), np.int8)
+    occ[::37, :] = 100
+    occ[:, ::53] = -1
+    rng = np.random.default_rng(11)
+    pts = np.ones((30000, 4), np.float32)
+    pts[:, 0] = rng.uniform(-5, 60, len(pts))
+    pts[:, 1] = rng.uniform(-5, 65, len(pts))
+    pts[:100, 0] = np.nan
+    pts[100:200, 1] = 1e30
+    trk.set_map(occ, 0.05, (0.0, 0.0), static_tolarance=1)
+    kept = trk.remove_static(pts)
+    ref, _ = oracle.remove_static(pts, occ, 0.05, (0.0, 0.0), static_tolerance=1)
+    assert np.array_equal(kept, ref)
+    assert len(trk.remove_static(np.zeros((0, 4), np.float32))) == 0
+
+
+def test_c1_frame_fused(trk, oracle, synth):
+    occ, res, origin = synth.make_map_c1()
+    cloud, _ = synth.make_frame_c1()
+    p = synth.C1_PARAMS
+    trk.set_map(occ, res, origin[:2], static_tolarance=p["static_tolerance"])
+    trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    out = trk.frame(cloud, stamp_minus_time_init=12.25)
+    kept_ref, _ = oracle.remove_static(cloud, occ, res, origin[:2], static_tolerance=p["static_tolerance"])
+    assert np.array_equal(out["kept"], kept_ref)
+    off_ref, idx_ref = oracle.cluster_kdtree(kept_ref, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    assert np.array_equal(out["offsets"], off_ref) and np.array_equal(out["indices"], idx_ref)
+    assert out["K"] >= 10
+    cen_ref = oracle.get_centroid(kept_ref, off_ref, idx_ref, 12.25)
+    np.testing.assert_allclose(out["centroids"], cen_ref, rtol=RTOL, atol=1e-6)
+    st_ref = oracle.cluster_stats(kept_ref, off_ref, idx_ref)
+    st = out["stats"]
+    assert np.array_equal(st["count"], st_ref[:, 0].astype(np.int32))
+    np.testing.assert_allclose(st["mean"], st_ref[:, 1:4], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(st["bbox_min"], st_ref[:, 4:7]) and np.array_equal(st["bbox_max"], st_ref[:, 7:10])
+
+
+def test_centroid_bitexact_small_clusters(trk, oracle):
+    # getCentroid is deterministic IEEE arithmetic in both implementations: expect identical bits
+    rng = np.random.default_rng(3)
+    parts = [np.asarray(c) + rng.normal(0, 0.15, size=(rng.integers(5, 120), 3)) for c in rng.uniform(-30, 30, size=(60, 3))]
+    pts = np.ones((sum(len(p) for p in parts), 4), np.float32)
+    pts[:, :3] = np.concatenate(parts)
+    trk.set_cluster_params(0.35, 3, 5000)
+    off, idx = trk.extract(pts)
+    cen = trk.get_centroid(3.0)
+    ref = oracle.get_centroid(pts, off, idx, 3.0)
+    assert len(off) - 1 > 20
+    assert np.array_equal(cen.view(np.uint32), ref.view(np.uint32))
+
+
+def test_c2_slice_vs_kdtree(trk, oracle, synth):
+    # a 64k azimuth wedge of the c2 frame, against the reference path (KD-tree + BFS)
+    p = synth.C2_PARAMS
+    frame = synth.scene_c2().frame(0)
+    wedge = frame[np.arctan2(frame[:, 1], frame[:, 0]) < -np.pi + 2 * np.pi / 16]
+    trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    off, idx = trk.extract(wedge)
+    off_ref, idx_ref = oracle.cluster_kdtree(wedge, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    assert np.array_equal(off, off_ref) and np.array_equal(idx, idx_ref)
+
+
+def test_c2_full_frame(trk, oracle, synth):
+    p = synth.C2_PARAMS
+    frame = synth.scene_c2().frame(0)
+    assert len(frame) == 1 << 20
+    off, idx = check_extract(trk, oracle, frame, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], brute=False)
+    # size-independent properties: indices ascending inside clusters, sizes descending, a partition of a subset
+    sizes = np.diff(off)
+    assert np.all(sizes[:-1] >= sizes[1:]) and sizes.min() >= p["min_cluster_size"] and sizes.max() <= p["max_cluster_size"]
+    assert len(np.unique(idx)) == len(idx)
+    for c in range(0, len(off) - 1, 17):
+        seg = idx[off[c]:off[c + 1]]
+        assert np.all(seg[1:] > seg[:-1])
+    st = trk.cluster_stats()
+    st_ref = oracle.cluster_stats(frame, off, idx)
+    np.testing.assert_allclose(st["mean"], st_ref[:, 1:4], rtol=RTOL, atol=1e-5)
+    assert np.array_equal(st["bbox_min"], st_ref[:, 4:7]) and np.array_equal(st["bbox_max"], st_ref[:, 7:10])
+    # idempotence: clustering the same frame again gives the same bytes
+    off2, idx2 = trk.extract(frame)
+    assert np.array_equal(off, off2) and np.array_equal(idx, idx2)
+
+
+@pytest.mark.parametrize("tol", [0.1, 0.3, 1.0])
+def test_c4_blobs(trk, oracle, synth, tol):
+    p = synth.C4_PARAMS
+    frame = synth.make_frame_c4(n_points=1 << 18, n_blobs=125)
+    check_extract(trk, oracle, frame, tol, p["min_cluster_size"], p["max_cluster_size"], brute=False)
+
+
+def test_batch_matches_single_frames(trk, oracle, synth):
+    p = synth.C3_PARAMS
+    sc = synth.scene_c3()
+    frames = [sc.frame(f, n_points=20000 + 1000 * f) for f in range(5)] + [np.zeros((0, 4), np.float32)]
+    trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    fco, off, idx = trk.extract_batch(frames)
+    assert fco[0] == 0 and fco[-1] == len(off) - 1
+    for f, fr in enumerate(frames):
+        o1, i1 = trk.extract(fr)
+        k0, k1 = fco[f], fco[f + 1]
+        assert k1 - k0 == len(o1) - 1
+        assert np.array_equal(off[k0:k1 + 1] - off[k0], o1)
+        assert np.array_equal(idx[off[k0]:off[k1]], i1)
+
+
+def test_many_clusters_large_k_path(trk, oracle):
+    # > 8192 clusters forces the 64-bit radix ordering path
+    rng = np.random.default_rng(5)
+    centres = np.stack(np.meshgrid(np.arange(110), np.arange(100), indexing="ij"), -1).reshape(-1, 2) * 2.0
+    pts = np.ones((len(centres) * 3, 4), np.float32)
+    pts[:, :2] = np.repeat(centres, 3, axis=0) + rng.uniform(-0.1, 0.1, (len(centres) * 3, 2))
+    pts[:, 2] = 0
+    pts = pts[rng.permutation(len(pts))]
+    pts = pts[: len(pts) - 500]  # some clusters lose points: sizes 1..3
+    off, idx = check_extract(trk, oracle, pts, 0.4, 2, 3, brute=False)
+    assert len(off) - 1 > 8192
+
+
+def test_ihgp_c5(trk, oracle, synth):
+    L, T = 40, 1000
+    hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
+    hyp_y = (np.exp(-5.0), np.exp(-3.0), np.exp(0.5))
+    trk.ihgp_configure(0.1, 0.03, hyp, hyp_y, L)
+    dt32 = float(np.float32(0.1))
+    cx, cy = oracle.ihgp_setup(dt32, *hyp), oracle.ihgp_setup(dt32, *hyp_y)
+    np.testing.assert_allclose(trk.ihgp_constants(0), cx, rtol=1e-12)
+    np.testing.assert_allclose(trk.ihgp_constants(1), cy, rtol=1e-12)
+    m_gpu, m_ref = np.zeros((T, 4)), np.zeros((T, 4))
+    for frame in range(3):  # the smoothed state is carried across frames
+        rings = synth.make_rings_c5(T, L, frame=frame)
+        pv = trk.ihgp_step(rings, m_gpu)
+        pv_ref = oracle.ihgp_step(rings, m_ref, 0.1, 0.03, cx, cy)
+        np.testing.assert_allclose(pv, pv_ref, rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(m_gpu, m_ref, rtol=RTOL, atol=1e-9)
+    assert np.abs(pv[:, 4:6]).max() <= 1.5
+
+
+def test_error_paths(mot, trk):
+    with pytest.raises(mot.MotError) as e:
+        trk.set_cluster_params(0.0, 1, 10)
+    assert e.value.code == -1
+    bad = np.ones((10, 4), np.float32)
+    bad[3, 1] = np.nan
+    trk.set_cluster_params(0.3, 1, 10)
+    with pytest.raises(mot.MotError) as e:
+        trk.extract(bad)
+    assert e.value.code == -6
+    small = mot.Tracker(device=0, max_points=100, max_tracks=0)
+    with pytest.raises(mot.MotError) as e:
+        small.extract(np.ones((101, 4), np.float32))
+    assert e.value.code == -3
+    with pytest.raises(mot.MotError) as e:
+        small.remove_static(np.ones((10, 4), np.float32))
+    assert e.value.code == -4
+    small.close()
