@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- Euclidean-clustering throughput of the B200 hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # one process per GPU under torchrun for N > 1
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload = "c2"): BASELINE config[1] -- 2^20-point 128-beam-style synthetic frames, cluster
+tolerance 0.5 m, min 5 / max 100000.  A "step" is one pass of the hot path (voxel grid build, union-find,
+size filter + CSR emission, per-cluster table) over a batch of `--frames` DISTINCT frames per GPU, one after the
+other; with the default 8 frames the step's inputs are 128 MiB > the 126 MB L2, so no frame is served from a
+warm L2.  N > 1: every rank clusters its own frames (weak scaling) and rank 0 gathers the cluster tables.
+
+value  = points/s with the frames already resident in HBM (mot_frame_device; CUDA events on the handle's stream).
+e2e    = the same metric through the reference-facing call mot_cluster() with pinned HOST buffers: H2D copy of
+         the cloud and D2H copy of the CSR result inside the timed region.
+The CPU oracle (oracle/) is only used for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "euclidean_clustering_throughput"
+UNIT = "Mpoints/s"
+
+
+def make_config(p, n_pts, F, world):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": "c2", "points_per_frame": n_pts, "frames_per_step_per_gpu": F, "cluster_tolerance": p["cluster_tolerance"],
+            "min_cluster_size": p["min_cluster_size"], "max_cluster_size": p["max_cluster_size"],
+            "l2_policy": f"{F} distinct frames per step ({F * n_pts * 16 >> 20} MiB of input > 126 MB L2)",
+            "parallelism": f"frames sharded over {world} GPU(s), tables gathered to rank 0" if world > 1 else "single GPU"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.f.close()
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = [float(r[0]) for r in rows if len(r) >= 8]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][1])
+                out["samples"] = len(sm)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for i, nme in enumerate(names):
+                    if any(r[4 + i].strip() == "Active" for r in rows if len(r) >= 8):
+                        out["reasons"].append(nme)
+        except Exception:
+            pass
+        return out
+
+
+def kernel_bytes(name, M, cf, cc, K, total, key_bytes, n_sort_passes, R_G=1024 * 592):
+    """ALGORITHMIC bytes one launch of `name` must move (per-point figures follow SURVEY 8d)."""
+    kb = key_bytes
+    table = {
+        "k_bbox": 16 * M,
+        "k_cell_keys": (16 + kb) * M,
+        "k_rs_hist[cells]": kb * M,
+        "k_rs_scatter[cells]": 2 * (kb + 4) * M,          # read pair + write pair (first pass synthesises the index)
+        "k_cells_count": (kb + 4 + 16 + 16) * M,          # key, index, gather point, write sorted SoA point
+        "k_cells_write": (kb + 4) * M + 24 * cf + 16 * cc,  # key, cell id per point, cell tables + hash insert
+        "k_uf_pairs<1>": 16 * M + 16 * cf + 12 * cc,      # every sorted point once + cell table + parent + hash
+        "k_uf_pairs<2>": 16 * cf + 12 * cc,               # cell-level only unless a witness search is needed
+        "k_uf_flatten<in-place>": 8 * cf,
+        "k_uf_flatten<root>": 8 * cf,
+        "k_comp_accumulate": 16 * cf,
+        "k_kept_list": 12 * cf + 12 * K,
+        "k_clusters_small": 24 * K,
+        "k_point_rank": (16 + 4 + 4 + 4) * M,             # sorted point (index in .w), cell id, key out, label out
+        "k_rs_hist[csr]": 4 * M,
+        "k_rs_scatter[csr]": 16 * M,
+        "k_cluster_stats": 20 * total + 40 * K,
+    }
+    return table.get(name)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    mot = entry.load_package()
+    synth = mot.synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    from importlib import import_module  # shard helpers live in the package
+    shard = import_module("mot_b200.shard")
+
+    p = synth.C2_PARAMS
+    scene = synth.scene_c2()
+    F = args.frames
+    frames_np = [scene.frame(rank * F + f) for f in range(F)]
+    n_pts = len(frames_np[0])
+    d_frames = [torch.from_numpy(fr).to(dev) for fr in frames_np]
+    trk = mot.Tracker(device=local_rank, max_points=n_pts, max_tracks=0)
+    trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+
+    table_buf = torch.zeros((F, 4096, 10), dtype=torch.float32, device=dev)
+
+    def step_device(gather):
+        launches, counts = 0, []
+        for f in range(F):
+            trk.frame_device(d_frames[f].data_ptr(), n_pts)
+            launches += trk.last_launches()
+            if gather:
+                M, K, total = trk.result_counts()
+                k = min(K, table_buf.shape[1])
+                trk.lib.mot_result_fetch(trk.h, None, 0, None, 0, None, 0, table_buf[f].data_ptr(), None, k) if k else None
+                counts.append(k)
+        if gather:
+            cnt = torch.tensor(counts, dtype=torch.int64, device=dev)
+            payload = torch.cat([table_buf[f, :counts[f]] for f in range(F)]) if sum(counts) else torch.zeros((0, 10), device=dev)
+            shard.gather_tables(cnt, payload, device=dev)
+        return launches
+
+    gather = world > 1
+    for _ in range(max(args.warmup, 3)):
+        step_device(gather)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    trk.timer_start()
+    launches = 0
+    for _ in range(args.steps):
+        launches += step_device(gather)
+    ms = trk.timer_stop()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, wall_max = float(t[0]), float(t[1])
+    pts_per_step = world * F * n_pts
+    value = pts_per_step * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through mot_cluster (pinned), copies inside the timed region ----
+    h_frames = [torch.from_numpy(fr).pin_memory() for fr in frames_np]
+    h_off = torch.empty(n_pts + 1, dtype=torch.int32).pin_memory()
+    h_idx = torch.empty(n_pts, dtype=torch.int32).pin_memory()
+    import ctypes as C
+    kk = C.c_int32(0)
+
+    def step_e2e():
+        d2h = 0
+        for f in range(F):
+            rc = trk.lib.mot_cluster(trk.h, h_frames[f].data_ptr(), n_pts, h_off.data_ptr(), n_pts + 1, h_idx.data_ptr(), n_pts, C.byref(kk))
+            assert rc == 0, trk.lib.mot_last_error(trk.h)
+            d2h += 4 * (kk.value + 1) + 4 * int(h_off[kk.value])
+        return d2h
+
+    for _ in range(3):
+        step_e2e()
+    if dist:
+        dist.barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    trk.timer_start()
+    d2h_bytes = 0
+    for _ in range(e2e_steps):
+        d2h_bytes += step_e2e()
+    e_ms = trk.timer_stop()
+    te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pts_per_step * e2e_steps / (float(te[0]) * 1e-3) / 1e6
+
+    # ---- per-kernel attribution (separate pass with event pairs around every launch) ----
+    trk.set_profiling(True)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        step_device(False)
+    prof = trk.profile()
+    trk.set_profiling(False)
+    M, K, total = trk.result_counts()
+    grid = trk.result_grid()
+    key_bytes = 4 if grid["key_bits"] <= 32 else 8
+    peak, peak_src = peaks()
+    kernels = []
+    tot_kernel_ms = sum(v[0] for v in prof.values())
+    for name, (tms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        avg_ms = tms / cnt
+        b = kernel_bytes(name, M, grid["fine_cells"], grid["coarse_cells"], K, total, key_bytes, 0)
+        kernels.append({"kernel": name, "launches_per_frame": cnt / (prof_steps * F), "avg_us": round(avg_ms * 1e3, 2),
+                        "share": round(tms / tot_kernel_ms, 4), "alg_bytes": b,
+                        "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None})
+    top = kernels[0]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(top["kernel"])
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(top["gbs"] / peak, 4) if top["gbs"] else None, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": top["alg_bytes"], "avg_launch_us": top["avg_us"], "share_of_kernel_time": top["share"]}
+    # whole-frame figure against SURVEY 8d's B_frame (no removeStatic at c2: N-term dropped)
+    P = (grid["key_bits"] + 9) // 10
+    b_frame = (152 + 16 * P) * M + 16 * grid["coarse_cells"] + 44 * K
+    frame_us = ms_max * 1e3 / (args.steps * F)
+    whole = {"alg_bytes_per_frame": b_frame, "frame_us": round(frame_us, 1), "gbs": round(b_frame / (frame_us * 1e-6) / 1e9, 1),
+             "frac": round(b_frame / (frame_us * 1e-6) / 1e9 / peak, 4)}
+
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": make_config(p, n_pts, F, world),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": F * n_pts * 16, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
+                "api": "mot_cluster (host pinned buffers in, CSR out)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "frame_roofline": whole,
+        "kernels": kernels[:12],
+        "wall_ms_per_step": round(wall_max / args.steps, 4),
+        "result": {"kept_points": M, "clusters": K, "indices": total, **grid},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(frames_np[0], p)
+    trk.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+def wedge(frame, frac):
+    az = np.arctan2(frame[:, 1], frame[:, 0])
+    return np.ascontiguousarray(frame[az < -np.pi + 2 * np.pi * frac])
+
+
+def cpu_baseline(frame, p):
+    """The oracle's restatement of the reference path (KD-tree built twice + BFS, 1 thread) on an azimuth wedge
+    of the same frame (same point density as the full frame; bounded to ~10-30 s of CPU work)."""
+    oracle = entry.load_oracle()
+    w = wedge(frame, 1.0 / 4)
+    t0 = time.perf_counter()
+    off, idx = oracle.cluster_kdtree(w, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], build_twice=True)
+    dt = time.perf_counter() - t0
+    return {"value": round(len(w) / dt / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1/4 azimuth wedge of frame 0 ({len(w)} points, {len(off) - 1} clusters), {dt:.1f} s, oracle KD-tree+BFS restatement of PCL"}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path.  PCL/FLANN cannot be built here, so this is the oracle
+    port (kind "port"): KD-tree (leaf 15) built twice + sorted radius search + serial BFS, one frame wedge per host
+    thread (frames are independent), all host threads."""
+    if rank != 0:
+        return None
+    from concurrent.futures import ThreadPoolExecutor
+
+    mot = entry.load_package()
+    oracle = entry.load_oracle()
+    synth = mot.synth
+    p = synth.C2_PARAMS
+    scene = synth.scene_c2()
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    base = [wedge(scene.frame(f), 1.0 / 16) for f in range(min(threads, 8))]
+    work = [base[i % len(base)] for i in range(threads)]
+    pts = sum(len(w) for w in work)
+
+    def one(w):
+        return oracle.cluster_kdtree(w, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], build_twice=True)
+
+    def step():
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, work))
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = pts * args.steps / dt / 1e6
+    sample = f"{threads} x 1/16 azimuth wedges of c2 frames ({pts} points per step), one wedge per host thread"
+    return {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": make_config(p, 1 << 20, args.frames, world),
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=8, help="distinct frames per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+    else:
+        out = run_b200(args, rank, world, local_rank)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

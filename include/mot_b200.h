@@ -115,11 +115,14 @@ int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remov
                      double stamp_minus_time_init);
 /* Counts of the last result: kept points, clusters, total indices. */
 int mot_result_counts(mot_handle* h, size_t* m, int32_t* n_clusters, size_t* n_indices);
+/* Grid statistics of the last result: occupied fine (clique) cells, occupied coarse cells, voxel key width. */
+int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, int32_t* key_bits);
 /* Device pointers of the last result (valid until the next call on the handle). */
 int mot_result_device_ptrs(mot_handle* h, const float** d_kept_xyz16, const int32_t** d_cluster_offsets,
                            const int32_t** d_point_indices, const mot_cluster_stat** d_stats,
                            const float** d_centroids_xyzi);
-/* Copies the last result to host buffers (any may be NULL). */
+/* Copies the last result to caller buffers (any may be NULL).  Destinations may be host or device pointers
+ * (cudaMemcpyDefault), so a rank can land its table straight in a buffer it is about to gather. */
 int mot_result_fetch(mot_handle* h, float* kept_xyz16, size_t kept_capacity, int32_t* cluster_offsets,
                      size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity,
                      mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity);
@@ -127,6 +130,20 @@ int mot_result_fetch(mot_handle* h, float* kept_xyz16, size_t kept_capacity, int
  * filter).  Debug/parity aid for partition checks at sizes where CSR comparison is unwieldy. */
 int mot_result_labels(mot_handle* h, int32_t* labels, size_t capacity);
 int mot_last_timings(mot_handle* h, mot_timings* t);
+
+/* Number of kernels the last frame / batch / IHGP call launched. */
+int mot_last_launches(mot_handle* h);
+
+/* Per-kernel profile: when on, every launch is bracketed by a CUDA event pair on the handle's stream and the
+ * durations accumulate per kernel id until the next mot_set_profiling call.  Off by default (events cost time). */
+int mot_set_profiling(mot_handle* h, int on);
+int mot_profile_kernels(void);
+const char* mot_profile_kernel_name(int kernel_id);
+int mot_profile_read(mot_handle* h, float* ms_total, int32_t* launches, int capacity);
+
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this handle is launched on). */
+int mot_timer_start(mot_handle* h);
+int mot_timer_stop(mot_handle* h, float* ms);
 
 /* Pins / unpins a caller-owned host buffer so copies run at full PCIe speed (optional). */
 int mot_host_register(void* ptr, size_t bytes);

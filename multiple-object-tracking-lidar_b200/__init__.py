@@ -87,10 +87,18 @@ SYMBOLS = {
                             C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, _SIZE]),
     "mot_frame_device": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_int, C.c_int, C.c_double]),
     "mot_result_counts": (C.c_int, [_H, C.POINTER(_SIZE), C.POINTER(C.c_int32), C.POINTER(_SIZE)]),
+    "mot_result_grid": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mot_result_device_ptrs": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 5),
     "mot_result_fetch": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, C.c_void_p, _SIZE]),
     "mot_result_labels": (C.c_int, [_H, C.c_void_p, _SIZE]),
     "mot_last_timings": (C.c_int, [_H, C.POINTER(Timings)]),
+    "mot_last_launches": (C.c_int, [_H]),
+    "mot_set_profiling": (C.c_int, [_H, C.c_int]),
+    "mot_profile_kernels": (C.c_int, []),
+    "mot_profile_kernel_name": (C.c_char_p, [C.c_int]),
+    "mot_profile_read": (C.c_int, [_H, _f32, _i32, C.c_int]),
+    "mot_timer_start": (C.c_int, [_H]),
+    "mot_timer_stop": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "mot_host_register": (C.c_int, [C.c_void_p, _SIZE]),
     "mot_host_unregister": (C.c_int, [C.c_void_p]),
     "mot_cluster_batch": (C.c_int, [_H, C.c_void_p, _i64, C.c_int, C.c_void_p, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
@@ -225,6 +233,11 @@ class Tracker:
         self._ck(self.lib.mot_result_counts(self.h, C.byref(m), C.byref(k), C.byref(t)))
         return m.value, k.value, t.value
 
+    def result_grid(self):
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.mot_result_grid(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(fine_cells=a.value, coarse_cells=b.value, key_bits=c.value)
+
     def result_device_ptrs(self):
         ps = [C.c_void_p() for _ in range(5)]
         self._ck(self.lib.mot_result_device_ptrs(self.h, *[C.byref(p) for p in ps]))
@@ -246,6 +259,28 @@ class Tracker:
         lab = np.empty(max(M, 1), dtype=np.int32)
         self._ck(self.lib.mot_result_labels(self.h, _ptr(lab), len(lab)))
         return lab[:M]
+
+    def last_launches(self):
+        return int(self.lib.mot_last_launches(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.mot_set_profiling(self.h, int(on)))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} accumulated since set_profiling(True)."""
+        n = self.lib.mot_profile_kernels()
+        ms = np.zeros(n, dtype=np.float32)
+        cnt = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.mot_profile_read(self.h, ms, cnt, n))
+        return {self.lib.mot_profile_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
+
+    def timer_start(self):
+        self._ck(self.lib.mot_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.mot_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def timings(self):
         t = Timings()

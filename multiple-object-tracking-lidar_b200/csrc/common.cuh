@@ -3,7 +3,40 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace mot {
+
+// Optional per-kernel timing (mot_set_profiling): a CUDA event pair around every launch on the handle's stream.
+// Off by default; bench.py switches it on for a separate pass to attribute the step time to kernels.
+struct Prof {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> pool;
+    struct Rec { int id; cudaEvent_t e0, e1; };
+    std::vector<Rec> recs;
+    size_t used = 0;
+    int launches = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void begin(int id) {
+        ++launches;
+        if (!on) return;
+        Rec r{id, get(), get()};
+        cudaEventRecord(r.e0, st);
+        recs.push_back(r);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(recs.back().e1, st);
+    }
+};
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -35,6 +35,20 @@ using namespace mot;
 static_assert(sizeof(mot_cluster_stat) == sizeof(ClusterStat), "stat layout");
 static_assert(sizeof(mot_cluster_stat) == 40, "stat layout");
 
+// kernel ids for the launch counter / per-kernel profile (mot_profile_read)
+enum KernelId {
+    KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_CELLS_WRITE,
+    KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
+    KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
+    KID_LOCALIZE, KID_STATS, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_N
+};
+static const char* const kKernelNames[KID_N] = {
+    "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
+    "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_comp_accumulate", "k_kept_list",
+    "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
+    "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
+    "k_cluster_stats", "k_farthest_pair", "k_circumcentre", "k_ihgp_step"};
+
 struct mot_handle {
     int device = 0;
     size_t max_points = 0, max_tracks = 0;
@@ -93,11 +107,23 @@ struct mot_handle {
     bool have_result = false;
     const float4* res_cloud = nullptr;  // the clustered cloud on the device (d_pts or the caller's pointer)
     int res_M = 0, res_K = 0, res_total = 0, res_idx_buf = 0, res_frames = 1;
+    int res_fine = 0, res_coarse = 0, res_key_bits = 0;
     bool res_centroids = false;
-    int launches = 0;
+    Prof prof;
+    float prof_ms[KID_N] = {};
+    int prof_n[KID_N] = {};
     cudaEvent_t ev[6] = {};
+    cudaEvent_t timer_ev[2] = {};
     mot_timings tim{};
 };
+
+// every kernel launch goes through LAUNCH: counts it and, when profiling is on, brackets it with an event pair
+#define LAUNCH(kid, ...)        \
+    do {                        \
+        h->prof.begin(kid);     \
+        __VA_ARGS__;            \
+        h->prof.end();          \
+    } while (0)
 
 namespace {
 
@@ -152,10 +178,9 @@ int enqueue_remove_static(mot_handle* h, const float4* d_src, int n) {
     const size_t bitmap_bytes = (size_t)((h->mp.n_words * 4 + 15) & ~15);
     const int use_smem = bitmap_bytes <= (size_t)RSK_SMEM_BITMAP_MAX ? 1 : 0;
     const size_t smem = use_smem ? bitmap_bytes : 0;
-    k_rs_count<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_bbox);
-    k_rs_compact<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_pts,
-                                                           h->d_counts + CNT_M);
-    h->launches += 2;
+    LAUNCH(KID_RS_COUNT, k_rs_count<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_bbox));
+    LAUNCH(KID_RS_COMPACT, k_rs_compact<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk,
+                                                                                  h->d_pts, h->d_counts + CNT_M));
     CK(cudaGetLastError());
     return MOT_OK;
 }
@@ -164,7 +189,7 @@ int reset_frame_state(mot_handle* h) {
     static const int bbox_init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
     CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), h->stream));
     CK(cudaMemcpyAsync(h->d_bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, h->stream));
-    h->launches = 0;
+    h->prof.launches = 0;
     h->have_result = false;
     return MOT_OK;
 }
@@ -177,9 +202,8 @@ template <typename KT>
 int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCodec& g, int total_bits, int n_frames) {
     cudaStream_t st = h->stream;
     KT* keys[2] = {reinterpret_cast<KT*>(h->d_keys[0]), reinterpret_cast<KT*>(h->d_keys[1])};
-    k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]);
-    h->launches += 1;
-    const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, &h->launches);
+    LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]));
+    const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, h->prof, KID_SORT_HIST);
     const KT* skeys = keys[sb];
     const uint32_t* svals = h->d_vals[sb];
 
@@ -195,11 +219,11 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     const int hshift = 32 - hb;
 
     const Chunking ck = make_chunking(M, CELL_THREADS, CELL_MAX_GRID);
-    k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk);
-    k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, M, ck.chunk, h->d_blk, h->d_fc_start, h->d_cc_first, h->d_pcell,
-                                                        h->d_parent, h->d_csize, h->d_cmin, h->d_crank, reinterpret_cast<KT*>(h->d_hkeys),
-                                                        h->d_hvals, hmask, hshift, h->d_counts);
-    h->launches += 2;
+    LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk));
+    LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, M, ck.chunk, h->d_blk, h->d_fc_start, h->d_cc_first,
+                                                                               h->d_pcell, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
+                                                                               reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
+                                                                               h->d_counts));
     CK(cudaEventRecord(h->ev[2], st));
 
     const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
@@ -207,13 +231,14 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (uf_grid > h->num_sms * 8) uf_grid = h->num_sms * 8;
     int flat_grid = (M + 255) / 256;
     if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
-    k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, reinterpret_cast<const KT*>(h->d_hkeys),
-                                                      h->d_hvals, hmask, hshift, h->d_counts, h->d_parent, g, r2);
-    k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts);
-    k_uf_pairs<KT, 2><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, reinterpret_cast<const KT*>(h->d_hkeys),
-                                                      h->d_hvals, hmask, hshift, h->d_counts, h->d_parent, g, r2);
-    k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts);
-    h->launches += 4;
+    LAUNCH(KID_UF1, k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
+                                                                      reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
+                                                                      h->d_counts, h->d_parent, g, r2));
+    LAUNCH(KID_FLATTEN1, k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+    LAUNCH(KID_UF2, k_uf_pairs<KT, 2><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
+                                                                      reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
+                                                                      h->d_counts, h->d_parent, g, r2));
+    LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
     CK(cudaEventRecord(h->ev[3], st));
     CK(cudaGetLastError());
     return MOT_OK;
@@ -225,8 +250,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         if (m_known > 0) {
             int grid = (m_known + 255) / 256;
             if (grid > h->num_sms * 8) grid = h->num_sms * 8;
-            k_bbox<<<grid, 256, 0, st>>>(cloud, m_known, h->d_bbox);
-            h->launches += 1;
+            LAUNCH(KID_BBOX, k_bbox<<<grid, 256, 0, st>>>(cloud, m_known, h->d_bbox));
         }
     }
     CK(cudaEventRecord(h->ev[1], st));
@@ -241,6 +265,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_total = 0;
     h->res_frames = n_frames;
     h->res_centroids = false;
+    h->res_fine = h->res_coarse = h->res_key_bits = 0;
     if (h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
     if (M == 0) {
         for (int i = 1; i < 6; ++i) CK(cudaEventRecord(h->ev[i], st));
@@ -287,10 +312,9 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     const int ckey_bits = kc.size_bits + kc.idx_bits + frame_bits;
     int cgrid = (M + 255) / 256;
     if (cgrid > h->num_sms * 8) cgrid = h->num_sms * 8;
-    k_comp_accumulate<<<cgrid, 256, 0, st>>>(h->d_fc_start, h->d_root, h->d_csize, h->d_cmin, h->d_counts);
-    k_kept_list<<<cgrid, 256, 0, st>>>(h->d_root, h->d_csize, h->d_cmin, h->d_frame_offsets, n_frames, h->min_size, h->max_size, kc,
-                                        h->d_ckeys[0], h->d_croots[0], h->d_counts);
-    h->launches += 2;
+    LAUNCH(KID_COMP_ACC, k_comp_accumulate<<<cgrid, 256, 0, st>>>(h->d_fc_start, h->d_root, h->d_csize, h->d_cmin, h->d_counts));
+    LAUNCH(KID_KEPT_LIST, k_kept_list<<<cgrid, 256, 0, st>>>(h->d_root, h->d_csize, h->d_cmin, h->d_frame_offsets, n_frames, h->min_size,
+                                                            h->max_size, kc, h->d_ckeys[0], h->d_croots[0], h->d_counts));
     // ---- S2 ----
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -298,32 +322,34 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     const int total = h->h_pinned[8 + CNT_TOTAL];
     h->res_K = K;
     h->res_total = total;
+    h->res_fine = h->h_pinned[8 + CNT_FINE];
+    h->res_coarse = h->h_pinned[8 + CNT_COARSE];
+    h->res_key_bits = total_bits;
 
     const uint64_t* sorted_ckeys = nullptr;
     if (K <= CL_SMALL_MAX) {
-        k_clusters_small<<<1, CL_SMALL_THREADS, CL_SMALL_SMEM, st>>>(h->d_ckeys[0], h->d_croots[0], K, kc, h->d_ckeys[1], h->d_crank, h->d_cl_offsets);
+        LAUNCH(KID_CL_SMALL, k_clusters_small<<<1, CL_SMALL_THREADS, CL_SMALL_SMEM, st>>>(h->d_ckeys[0], h->d_croots[0], K, kc, h->d_ckeys[1],
+                                                                                         h->d_crank, h->d_cl_offsets));
         sorted_ckeys = h->d_ckeys[1];
-        h->launches += 1;
     } else {
-        const int cb = radix_sort_pairs<uint64_t>(st, h->d_ckeys, h->d_croots, K, ckey_bits, false, h->rws, &h->launches);
+        const int cb = radix_sort_pairs<uint64_t>(st, h->d_ckeys, h->d_croots, K, ckey_bits, false, h->rws, h->prof, KID_CLSORT_HIST);
         const Chunking ck = make_chunking(K, CLF_THREADS, CLF_MAX_GRID);
-        k_clusters_count<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], K, ck.chunk, kc, h->d_blk);
-        k_clusters_finalize<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], h->d_croots[cb], K, ck.chunk, kc, h->d_blk, h->d_crank, h->d_cl_offsets);
+        LAUNCH(KID_CL_COUNT, k_clusters_count<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], K, ck.chunk, kc, h->d_blk));
+        LAUNCH(KID_CL_FINALIZE, k_clusters_finalize<<<ck.grid, CLF_THREADS, 0, st>>>(h->d_ckeys[cb], h->d_croots[cb], K, ck.chunk, kc, h->d_blk,
+                                                                                    h->d_crank, h->d_cl_offsets));
         sorted_ckeys = h->d_ckeys[cb];
-        h->launches += 2;
     }
     if (n_frames > 1) {
-        k_frame_cluster_offsets<<<(n_frames + 1 + 127) / 128, 128, 0, st>>>(sorted_ckeys, K, kc, n_frames, h->d_frame_cl_offsets);
-        h->launches += 1;
+        LAUNCH(KID_FRAME_CL_OFF, k_frame_cluster_offsets<<<(n_frames + 1 + 127) / 128, 128, 0, st>>>(sorted_ckeys, K, kc, n_frames,
+                                                                                                    h->d_frame_cl_offsets));
     }
     // ---- CSR emission: stable partition of 0..M-1 by cluster rank ----
     uint32_t* pk[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
-    k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_pcell, h->d_root, h->d_crank, h->d_cmin, M, K, pk[0], h->d_labels);
-    h->launches += 1;
-    h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, &h->launches);
+    LAUNCH(KID_POINT_RANK, k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_pcell, h->d_root, h->d_crank, h->d_cmin, M, K, pk[0],
+                                                                        h->d_labels));
+    h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, h->prof, KID_PART_HIST);
     if (n_frames > 1 && total > 0) {
-        k_localize_indices<<<(total + 255) / 256, 256, 0, st>>>(h->d_vals[h->res_idx_buf], total, h->d_frame_offsets, n_frames);
-        h->launches += 1;
+        LAUNCH(KID_LOCALIZE, k_localize_indices<<<(total + 255) / 256, 256, 0, st>>>(h->d_vals[h->res_idx_buf], total, h->d_frame_offsets, n_frames));
     }
     CK(cudaEventRecord(h->ev[4], st));
 
@@ -338,13 +364,12 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         rc = ensure_tables(h, (size_t)K, with_centroids ? (size_t)K * slabs : 0);
         if (rc != MOT_OK) return rc;
         int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
-        k_cluster_stats<<<sgrid, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, h->d_stats);
-        h->launches += 1;
+        LAUNCH(KID_STATS, k_cluster_stats<<<sgrid, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, h->d_stats));
         if (with_centroids) {
-            k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands);
-            k_circumcentre<<<sgrid, CC_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands, (float)stamp,
-                                                         h->d_centroids);
-            h->launches += 2;
+            LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
+                                                                                       h->d_cands));
+            LAUNCH(KID_CIRCUMCENTRE, k_circumcentre<<<sgrid, CC_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
+                                                                                 h->d_cands, (float)stamp, h->d_centroids));
             h->res_centroids = true;
         }
     }
@@ -352,6 +377,19 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     CK(cudaGetLastError());
     h->have_result = true;
     return MOT_OK;
+}
+
+// accumulate the per-kernel event pairs of the call that just finished (stream already synchronised)
+void fold_profile(mot_handle* h) {
+    if (h->prof.on) {
+        for (auto& r : h->prof.recs) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { h->prof_ms[r.id] += ms; h->prof_n[r.id] += 1; }
+        }
+        cudaGetLastError();
+    }
+    h->prof.recs.clear();
+    h->prof.used = 0;
 }
 
 int finish_timings(mot_handle* h) {
@@ -370,6 +408,7 @@ int finish_timings(mot_handle* h) {
     h->tim.cluster_table_ms = t34;
     h->tim.reduce_ms = t45;
     h->tim.total_ms = t05;
+    fold_profile(h);
     return MOT_OK;
 }
 
@@ -379,25 +418,25 @@ int fetch_result(mot_handle* h, float* kept, size_t kept_cap, int32_t* offs, siz
     cudaStream_t st = h->stream;
     if (kept) {
         if (kept_cap < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "kept cloud buffer too small");
-        if (h->res_M) CK(cudaMemcpyAsync(kept, h->res_cloud, (size_t)h->res_M * 16, cudaMemcpyDeviceToHost, st));
+        if (h->res_M) CK(cudaMemcpyAsync(kept, h->res_cloud, (size_t)h->res_M * 16, cudaMemcpyDefault, st));
     }
     if (offs) {
         if (offs_cap < (size_t)h->res_K + 1) return fail(h, MOT_ERR_CAPACITY, "cluster_offsets buffer too small");
-        CK(cudaMemcpyAsync(offs, h->d_cl_offsets, ((size_t)h->res_K + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(offs, h->d_cl_offsets, ((size_t)h->res_K + 1) * 4, cudaMemcpyDefault, st));
     }
     if (idx) {
         if (idx_cap < (size_t)h->res_total) return fail(h, MOT_ERR_CAPACITY, "point_indices buffer too small");
-        if (h->res_total) CK(cudaMemcpyAsync(idx, h->d_vals[h->res_idx_buf], (size_t)h->res_total * 4, cudaMemcpyDeviceToHost, st));
+        if (h->res_total) CK(cudaMemcpyAsync(idx, h->d_vals[h->res_idx_buf], (size_t)h->res_total * 4, cudaMemcpyDefault, st));
     }
     if (stats && h->res_K) {
         if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "stats buffer too small");
         if (h->res_frames != 1) return fail(h, MOT_ERR_STATE, "per-cluster tables are not produced in batch mode");
-        CK(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->res_K * sizeof(ClusterStat), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->res_K * sizeof(ClusterStat), cudaMemcpyDefault, st));
     }
     if (cent && h->res_K) {
         if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "centroid buffer too small");
         if (!h->res_centroids) return fail(h, MOT_ERR_STATE, "centroids were not computed for the last result");
-        CK(cudaMemcpyAsync(cent, h->d_centroids, (size_t)h->res_K * 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cent, h->d_centroids, (size_t)h->res_K * 16, cudaMemcpyDefault, st));
     }
     CK(cudaStreamSynchronize(st));
     return MOT_OK;
@@ -423,9 +462,10 @@ int compute_centroids_late(mot_handle* h, double stamp) {
     int rc = ensure_tables(h, (size_t)K, (size_t)K * slabs);
     if (rc != MOT_OK) return rc;
     const int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
-    k_farthest_pair<<<K * slabs, FP_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands);
-    k_circumcentre<<<sgrid, CC_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs, h->d_cands, (float)stamp,
-                                                        h->d_centroids);
+    LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K,
+                                                                                      slabs, h->d_cands));
+    LAUNCH(KID_CIRCUMCENTRE, k_circumcentre<<<sgrid, CC_THREADS, 0, h->stream>>>(h->res_cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
+                                                                                h->d_cands, (float)stamp, h->d_centroids));
     CK(cudaGetLastError());
     h->res_centroids = true;
     return MOT_OK;
@@ -490,6 +530,8 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_frame_cl_offsets, h->frame_capacity + 2));
         CK(cudaMemset(h->d_frame_offsets, 0, (h->frame_capacity + 2) * sizeof(int)));
         for (auto& e : h->ev) CK(cudaEventCreate(&e));
+        for (auto& e : h->timer_ev) CK(cudaEventCreate(&e));
+        h->prof.st = h->stream;
         CK(rs_configure<uint32_t>());
         CK(rs_configure<uint64_t>());
         CK(cudaFuncSetAttribute(k_clusters_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMALL_SMEM));
@@ -525,6 +567,9 @@ int mot_destroy(mot_handle* h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : h->timer_ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : h->prof.pool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOT_OK;
@@ -700,6 +745,15 @@ int mot_result_counts(mot_handle* h, size_t* m, int32_t* n_clusters, size_t* n_i
     return MOT_OK;
 }
 
+int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, int32_t* key_bits) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    if (fine_cells) *fine_cells = h->res_fine;
+    if (coarse_cells) *coarse_cells = h->res_coarse;
+    if (key_bits) *key_bits = h->res_key_bits;
+    return MOT_OK;
+}
+
 int mot_result_device_ptrs(mot_handle* h, const float** d_kept, const int32_t** d_offsets, const int32_t** d_indices,
                            const mot_cluster_stat** d_stats, const float** d_centroids) {
     if (!h) return MOT_ERR_INVALID;
@@ -743,6 +797,38 @@ int mot_host_register(void* ptr, size_t bytes) {
 int mot_host_unregister(void* ptr) {
     if (!ptr) return MOT_ERR_INVALID;
     return cudaHostUnregister(ptr) == cudaSuccess ? MOT_OK : MOT_ERR_CUDA;
+}
+
+int mot_last_launches(mot_handle* h) { return h ? h->prof.launches : MOT_ERR_INVALID; }
+
+int mot_set_profiling(mot_handle* h, int on) {
+    if (!h) return MOT_ERR_INVALID;
+    h->prof.on = on != 0;
+    std::memset(h->prof_ms, 0, sizeof(h->prof_ms));
+    std::memset(h->prof_n, 0, sizeof(h->prof_n));
+    return MOT_OK;
+}
+int mot_profile_kernels(void) { return KID_N; }
+const char* mot_profile_kernel_name(int kid) { return kid >= 0 && kid < KID_N ? kKernelNames[kid] : ""; }
+int mot_profile_read(mot_handle* h, float* ms_total, int32_t* launches, int capacity) {
+    if (!h || !ms_total || !launches || capacity < KID_N) return MOT_ERR_INVALID;
+    for (int i = 0; i < KID_N; ++i) { ms_total[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; }
+    return MOT_OK;
+}
+
+int mot_timer_start(mot_handle* h) {
+    if (!h) return MOT_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->timer_ev[0], h->stream));
+    return MOT_OK;
+}
+int mot_timer_stop(mot_handle* h, float* ms) {
+    if (!h || !ms) return MOT_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->timer_ev[1], h->stream));
+    CK(cudaEventSynchronize(h->timer_ev[1]));
+    CK(cudaEventElapsedTime(ms, h->timer_ev[0], h->timer_ev[1]));
+    return MOT_OK;
 }
 
 // ---- batches -------------------------------------------------------------------------------------------------
@@ -893,18 +979,20 @@ int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_sta
         h->ring_capacity = h->max_tracks * (size_t)L;
     }
     cudaStream_t st = h->stream;
+    h->prof.launches = 0;
     CK(cudaMemcpyAsync(h->d_rings, rings, ring_elems * 16, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_mstate, m_state, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (n_tracks + IHGP_WARPS - 1) / IHGP_WARPS;
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
-    k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0], h->ihgp_axis[1],
-                                                     h->d_mstate, h->d_posvel);
+    LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0],
+                                                                      h->ihgp_axis[1], h->d_mstate, h->d_posvel));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    fold_profile(h);
     return MOT_OK;
 }
 

@@ -222,10 +222,10 @@ inline cudaError_t rs_configure() {
 
 // Sorts n pairs by the low `key_bits` bits of the key.  Input in (k[0], v[0]) -- v[0] is ignored and treated
 // as 0..n-1 when iota_first.  Returns the index (0/1) of the buffer pair that holds the result.
-// *launches is incremented by the number of kernels enqueued.
+// Every launch goes through prof (launch counter + optional event timing); kernel ids kid_base + {0,1,2}.
 template <typename KT>
 inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, int key_bits, bool iota_first,
-                            const RadixWorkspace& ws, int* launches) {
+                            const RadixWorkspace& ws, Prof& prof, int kid_base) {
     if (key_bits < 1) key_bits = 1;
     const int passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
     const int base = key_bits / passes, rem = key_bits % passes;
@@ -234,14 +234,19 @@ inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, in
     for (int p = 0; p < passes; ++p) {
         const int bits = base + (p < rem ? 1 : 0);
         const int R = 1 << bits;
+        prof.begin(kid_base);
         k_rs_hist<KT><<<ck.grid, RS_THREADS, R * sizeof(unsigned), st>>>(k[cur], n, ck.chunk, shift, bits, ws.hist);
+        prof.end();
+        prof.begin(kid_base + 1);
         k_rs_scan<<<(R + 7) / 8, 256, 0, st>>>(ws.hist, ws.prefix, ws.tot, R, ck.grid);
+        prof.end();
         const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT));
+        prof.begin(kid_base + 2);
         if (p == 0 && iota_first)
             k_rs_scatter<KT, true><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
         else
             k_rs_scatter<KT, false><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
-        if (launches) *launches += 3;
+        prof.end();
         cur ^= 1;
         shift += bits;
     }
