@@ -176,13 +176,13 @@ __global__ void k_frame_cluster_offsets(const uint64_t* __restrict__ ckeys, int 
 
 // Cluster rank of every point, scattered back to original point order (key of the final stable partition),
 // plus the component label (smallest original index of the component) for partition checks.
-__global__ void __launch_bounds__(256) k_point_rank(const float4* __restrict__ spts, const int* __restrict__ pcell, const int* __restrict__ root,
+__global__ void __launch_bounds__(256) k_point_rank(const float4* __restrict__ spts, const uint32_t* __restrict__ svals, const int* __restrict__ root,
                                                      const int* __restrict__ crank, const int* __restrict__ cmin, int m, int K,
                                                      uint32_t* __restrict__ pkey, int* __restrict__ labels) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const int orig = __float_as_int(spts[j].w);
-    const int r = root[pcell[j]];
+    const int orig = (int)svals[j];                          // sorted position -> original index
+    const int r = root[__float_as_int(spts[j].w)];           // .w = fine cell id
     const int k = crank[r];
     pkey[orig] = k < 0 ? (uint32_t)K : (uint32_t)k;
     labels[orig] = cmin[r];
@@ -196,50 +196,134 @@ __global__ void __launch_bounds__(256) k_localize_indices(uint32_t* __restrict__
     idx[t] = (uint32_t)(g - frame_offsets[frame_of(frame_offsets, n_frames, g)]);
 }
 
-// ---- K7: segmented reduction, one CTA per cluster over its (ascending) index list -----------------------------
+// ---- K7: segmented reduction over the CSR index list ----------------------------------------------------------
+// Point-parallel: a warp walks 32 consecutive CSR entries at a time.  While the whole group lies inside one cluster
+// the lanes just accumulate in registers; a group that straddles cluster boundaries is reduced with a segmented
+// warp scan.  Partial results go to per-cluster accumulators (fp64 sums, ordered-int min/max), so the cost is
+// independent of the cluster-size distribution (one 800k-point cluster or 100k tiny ones).
 struct ClusterStat {  // == mot_cluster_stat
     int count;
     float mean[3], bmin[3], bmax[3];
 };
-constexpr int STAT_THREADS = 128;
-__global__ void __launch_bounds__(STAT_THREADS) k_cluster_stats(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
-                                                                 const uint32_t* __restrict__ indices, int K, ClusterStat* __restrict__ out) {
-    __shared__ double ssum[STAT_THREADS / 32][3];
-    __shared__ float smin[STAT_THREADS / 32][3], smax[STAT_THREADS / 32][3];
-    for (int c = blockIdx.x; c < K; c += gridDim.x) {
-        const int s = cl_offsets[c], e = cl_offsets[c + 1];
-        double sum[3] = {0, 0, 0};
-        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (int t = s + threadIdx.x; t < e; t += STAT_THREADS) {
-            const float4 p = pts[indices[t]];
-            sum[0] += (double)p.x; sum[1] += (double)p.y; sum[2] += (double)p.z;
-            mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
-            mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+struct StatAcc {       // 48 bytes per cluster
+    double sum[3];
+    int mn[3], mx[3];  // float_to_ordered encoded
+};
+__global__ void __launch_bounds__(256) k_stats_init(StatAcc* __restrict__ acc, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    StatAcc a;
+    for (int d = 0; d < 3; ++d) { a.sum[d] = 0.0; a.mn[d] = 0x7fffffff; a.mx[d] = (int)0x80000000; }
+    acc[k] = a;
+}
+
+__device__ __forceinline__ void stat_flush(StatAcc* acc, int cid, double s0, double s1, double s2, float n0, float n1, float n2, float x0,
+                                           float x1, float x2) {
+    atomicAdd(&acc[cid].sum[0], s0); atomicAdd(&acc[cid].sum[1], s1); atomicAdd(&acc[cid].sum[2], s2);
+    atomicMin(&acc[cid].mn[0], float_to_ordered(n0)); atomicMin(&acc[cid].mn[1], float_to_ordered(n1)); atomicMin(&acc[cid].mn[2], float_to_ordered(n2));
+    atomicMax(&acc[cid].mx[0], float_to_ordered(x0)); atomicMax(&acc[cid].mx[1], float_to_ordered(x1)); atomicMax(&acc[cid].mx[2], float_to_ordered(x2));
+}
+
+constexpr int STAT_THREADS = 256;
+constexpr int STAT_GROUPS_PER_WARP = 16;  // 512 CSR entries per warp
+__global__ void __launch_bounds__(STAT_THREADS) k_stats_accumulate(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
+                                                                    const uint32_t* __restrict__ indices, int K, int total,
+                                                                    StatAcc* __restrict__ acc) {
+    const int lane = lane_id();
+    const int warp_global = blockIdx.x * (STAT_THREADS / 32) + warp_id();
+    const int t_begin = warp_global * (32 * STAT_GROUPS_PER_WARP);
+    if (t_begin >= total) return;
+    int cur = -1, cur_end = 0;  // warp-uniform: cluster whose points the lane accumulators currently hold
+    double s0 = 0, s1 = 0, s2 = 0;
+    float n0 = INFINITY, n1 = INFINITY, n2 = INFINITY, x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY;
+    for (int gidx = 0; gidx < STAT_GROUPS_PER_WARP; ++gidx) {
+        const int t0 = t_begin + gidx * 32;
+        if (t0 >= total) break;
+        const int t = t0 + lane;
+        const bool valid = t < total;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) p = pts[indices[t]];
+        const int last = min(t0 + 31, total - 1);
+        if (cur >= 0 && last < cur_end) {  // whole group inside the current cluster
+            if (valid) {
+                s0 += (double)p.x; s1 += (double)p.y; s2 += (double)p.z;
+                n0 = fminf(n0, p.x); n1 = fminf(n1, p.y); n2 = fminf(n2, p.z);
+                x0 = fmaxf(x0, p.x); x1 = fmaxf(x1, p.y); x2 = fmaxf(x2, p.z);
+            }
+            continue;
         }
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
+        // flush what the lanes hold for `cur`
+        if (cur >= 0) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                sum[d] += __shfl_xor_sync(kFull, sum[d], o);
-                mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
-                mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
+                s0 += __shfl_xor_sync(kFull, s0, o); s1 += __shfl_xor_sync(kFull, s1, o); s2 += __shfl_xor_sync(kFull, s2, o);
+                n0 = fminf(n0, __shfl_xor_sync(kFull, n0, o)); n1 = fminf(n1, __shfl_xor_sync(kFull, n1, o)); n2 = fminf(n2, __shfl_xor_sync(kFull, n2, o));
+                x0 = fmaxf(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(kFull, x1, o)); x2 = fmaxf(x2, __shfl_xor_sync(kFull, x2, o));
             }
-        __syncthreads();
-        if (lane_id() == 0)
-            for (int d = 0; d < 3; ++d) { ssum[warp_id()][d] = sum[d]; smin[warp_id()][d] = mn[d]; smax[warp_id()][d] = mx[d]; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            ClusterStat st;
-            st.count = e - s;
-            for (int d = 0; d < 3; ++d) {
-                double a = 0; float lo = INFINITY, hi = -INFINITY;
-                for (int w = 0; w < STAT_THREADS / 32; ++w) { a += ssum[w][d]; lo = fminf(lo, smin[w][d]); hi = fmaxf(hi, smax[w][d]); }
-                st.mean[d] = (float)(a / (double)(e - s));
-                st.bmin[d] = lo; st.bmax[d] = hi;
-            }
-            out[c] = st;
+            if (lane == 0) stat_flush(acc, cur, s0, s1, s2, n0, n1, n2, x0, x1, x2);
         }
+        // cluster of every entry of the group: largest k with cl_offsets[k] <= t
+        int cid = -1;
+        if (valid) {
+            int lo = cur >= 0 ? cur : 0, hi = K - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (cl_offsets[mid] <= t) lo = mid; else hi = mid - 1;
+            }
+            cid = lo;
+        }
+        // segmented inclusive scan over lanes (segments = runs of equal cid; cid is non-decreasing across lanes)
+        double a0 = (double)p.x, a1 = (double)p.y, a2 = (double)p.z;
+        float m0 = valid ? p.x : INFINITY, m1 = valid ? p.y : INFINITY, m2 = valid ? p.z : INFINITY;
+        float y0 = valid ? p.x : -INFINITY, y1 = valid ? p.y : -INFINITY, y2 = valid ? p.z : -INFINITY;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int oc = __shfl_up_sync(kFull, cid, o);
+            const double b0 = __shfl_up_sync(kFull, a0, o), b1 = __shfl_up_sync(kFull, a1, o), b2 = __shfl_up_sync(kFull, a2, o);
+            const float c0 = __shfl_up_sync(kFull, m0, o), c1 = __shfl_up_sync(kFull, m1, o), c2 = __shfl_up_sync(kFull, m2, o);
+            const float d0 = __shfl_up_sync(kFull, y0, o), d1 = __shfl_up_sync(kFull, y1, o), d2 = __shfl_up_sync(kFull, y2, o);
+            if (lane >= o && oc == cid) {
+                a0 += b0; a1 += b1; a2 += b2;
+                m0 = fminf(m0, c0); m1 = fminf(m1, c1); m2 = fminf(m2, c2);
+                y0 = fmaxf(y0, d0); y1 = fmaxf(y1, d1); y2 = fmaxf(y2, d2);
+            }
+        }
+        const int next_cid = __shfl_down_sync(kFull, cid, 1);
+        const bool tail = valid && (lane == 31 || next_cid != cid);
+        const int last_cid = __shfl_sync(kFull, cid, last - t0);
+        // the last segment stays in registers (lane `last - t0` holds its reduction) if the cluster continues
+        const bool keep = tail && cid == last_cid;
+        if (tail && !keep) stat_flush(acc, cid, a0, a1, a2, m0, m1, m2, y0, y1, y2);
+        cur = last_cid;
+        cur_end = cl_offsets[cur + 1];
+        s0 = keep ? a0 : 0.0; s1 = keep ? a1 : 0.0; s2 = keep ? a2 : 0.0;
+        n0 = keep ? m0 : INFINITY; n1 = keep ? m1 : INFINITY; n2 = keep ? m2 : INFINITY;
+        x0 = keep ? y0 : -INFINITY; x1 = keep ? y1 : -INFINITY; x2 = keep ? y2 : -INFINITY;
     }
+    if (cur >= 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(kFull, s0, o); s1 += __shfl_xor_sync(kFull, s1, o); s2 += __shfl_xor_sync(kFull, s2, o);
+            n0 = fminf(n0, __shfl_xor_sync(kFull, n0, o)); n1 = fminf(n1, __shfl_xor_sync(kFull, n1, o)); n2 = fminf(n2, __shfl_xor_sync(kFull, n2, o));
+            x0 = fmaxf(x0, __shfl_xor_sync(kFull, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(kFull, x1, o)); x2 = fmaxf(x2, __shfl_xor_sync(kFull, x2, o));
+        }
+        if (lane == 0) stat_flush(acc, cur, s0, s1, s2, n0, n1, n2, x0, x1, x2);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_stats_finalize(const StatAcc* __restrict__ acc, const int* __restrict__ cl_offsets, int K,
+                                                         ClusterStat* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const StatAcc a = acc[k];
+    ClusterStat st;
+    st.count = cl_offsets[k + 1] - cl_offsets[k];
+    for (int d = 0; d < 3; ++d) {
+        st.mean[d] = (float)(a.sum[d] / (double)st.count);
+        st.bmin[d] = ordered_to_float_bits(a.mn[d]);
+        st.bmax[d] = ordered_to_float_bits(a.mx[d]);
+    }
+    out[k] = st;
 }
 
 // ---- K8: the reference's getCentroid (MOT.cpp:708-822) ----------------------------------------------------------

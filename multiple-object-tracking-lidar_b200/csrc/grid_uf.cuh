@@ -124,21 +124,14 @@ __device__ __forceinline__ int hash_find(const KT* __restrict__ hkeys, const int
 constexpr int CELL_THREADS = 256;
 constexpr int CELL_MAX_GRID = 592;
 
-// counts[0][b] = fine-cell heads in block b's chunk, counts[1][b] = coarse-cell heads.  Also gathers the
-// sorted SoA point array: spts[j] = (x, y, z, bits(original index)).
+// counts[0][b] = fine-cell heads in block b's chunk, counts[1][b] = coarse-cell heads.
 template <typename KT>
-__global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restrict__ skeys, const uint32_t* __restrict__ svals,
-                                                               const float4* __restrict__ pts, float4* __restrict__ spts, int m,
-                                                               int chunk, int* __restrict__ counts) {
+__global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restrict__ skeys, int m, int chunk, int* __restrict__ counts) {
     __shared__ int red[2][CELL_THREADS / 32];
     const int begin = blockIdx.x * chunk, end = min(m, begin + chunk);
     int nf = 0, nc = 0;
     for (int j = begin + threadIdx.x; j < end; j += CELL_THREADS) {
         const KT k = skeys[j];
-        const uint32_t o = svals[j];
-        float4 p = pts[o];
-        p.w = __int_as_float((int)o);
-        spts[j] = p;
         if (j == 0) { ++nf; ++nc; }
         else {
             const KT kp = skeys[j - 1];
@@ -158,12 +151,13 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restri
 }
 
 // d_counts layout (ints): [0] fine cells, [1] coarse cells, [2] kept clusters, [3] kept points, [4] flags
-enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_N = 8 };
+enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_N = 8 };
 
 template <typename KT>
-__global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restrict__ skeys, const uint32_t* __restrict__ svals, int m,
+__global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restrict__ skeys, const uint32_t* __restrict__ svals,
+                                                               const float4* __restrict__ pts, float4* __restrict__ spts, int m,
                                                                int chunk, const int* __restrict__ counts, int* __restrict__ fc_start,
-                                                               int* __restrict__ cc_first, int* __restrict__ pcell,
+                                                               int* __restrict__ cc_first,
                                                                int* __restrict__ parent, int* __restrict__ csize, int* __restrict__ cmin,
                                                                int* __restrict__ crank, KT* __restrict__ hkeys, int* __restrict__ hvals,
                                                                unsigned hmask, int hshift, int* __restrict__ d_counts) {
@@ -189,7 +183,10 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
         const int excl = block_exclusive_scan(packed, scratch, &total);
         const int fi = fbase + (excl & 0xffff) + fh - 1;  // index of the fine cell containing j
         if (j < end) {
-            pcell[j] = fi;
+            // sorted SoA point: (x, y, z, bits(fine cell id)) -- the union-find kernels get a point's cell for free
+            float4 p = pts[svals[j]];
+            p.w = __int_as_float(fi);
+            spts[j] = p;
             if (fh) {
                 fc_start[fi] = j;
                 parent[fi] = fi;
@@ -341,6 +338,306 @@ __global__ void __launch_bounds__(UF_THREADS) k_uf_pairs(const KT* __restrict__ 
             }
         }
         __syncwarp();
+    }
+}
+
+// ---- K4 (v2): one warp per COARSE cell, points staged by TMA, local union-find in shared memory ----------------
+//
+// Record of an occupied coarse cell: x = first sorted point, y = point count, z = first fine cell, w = bit mask
+// of its occupied fine children (child code = fz<<2 | fy<<1 | fx).  The fine children are consecutive fine-cell
+// ids in child-code order, so fine id = z + rank of the child inside the mask.
+// Also resolves the half stencil once: nbr[ci*16 + c] = index of the coarse cell at stencil offset 13 + c
+// (c = 0 is ci itself, -1 = unoccupied), so the union-find warps start from one coalesced row load instead of
+// a key -> hash -> value -> record chain.  16 threads per coarse cell.
+template <typename KT>
+__global__ void __launch_bounds__(256) k_coarse_records(const KT* __restrict__ skeys, const int* __restrict__ fc_start,
+                                                         const int* __restrict__ cc_first, const int* __restrict__ d_counts,
+                                                         const KT* __restrict__ hkeys, const int* __restrict__ hvals, unsigned hmask, int hshift,
+                                                         GridCodec g, int4* __restrict__ crec, int* __restrict__ nbr) {
+    const int n_coarse = d_counts[CNT_COARSE];
+    const int sub = threadIdx.x & 15;
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; ci < n_coarse; ci += (gridDim.x * blockDim.x) >> 4) {
+        const int f0 = cc_first[ci];
+        const int p0 = fc_start[f0];
+        KT ck = skeys[p0] >> 3;
+        if (sub == 0) {
+            const int f1 = cc_first[ci + 1];
+            const int p1 = fc_start[f1];
+            unsigned mask = 0;
+            for (int f = f0; f < f1; ++f) mask |= 1u << (unsigned)(skeys[fc_start[f]] & 7);
+            crec[ci] = make_int4(p0, p1 - p0, f0, (int)mask);
+            nbr[ci * 16] = ci;
+        } else {
+            int nci = -1;
+            if (sub < 14) {
+                const int cxa = (int)(ck & (((KT)1 << g.bx) - 1)); ck >>= g.bx;
+                const int cya = (int)(ck & (((KT)1 << g.by) - 1)); ck >>= g.by;
+                const int cza = (int)(ck & (((KT)1 << g.bz) - 1)); ck >>= g.bz;
+                const int frame = (int)ck;
+                const int sidx = 13 + sub;
+                const int cx = cxa + (sidx % 3) - 1, cy = cya + ((sidx / 3) % 3) - 1, cz = cza + (sidx / 9) - 1;
+                if (cx >= 0 && cy >= 0 && cz >= 0 && cx < g.ncx && cy < g.ncy && cz < g.ncz)
+                    nci = hash_find<KT>(hkeys, hvals, hmask, hshift, coarse_compose<KT>(g, frame, cx, cy, cz));
+            }
+            nbr[ci * 16 + sub] = nci;
+        }
+    }
+}
+
+constexpr int UFC_THREADS = 256;
+constexpr int UFC_WARPS = UFC_THREADS / 32;
+constexpr int UFC_TILE_PTS = 256;   // points of the forward neighbourhood staged per warp (4 KB)
+constexpr int UFC_CELLS = 14;       // half stencil: the coarse cell itself + its 13 "forward" neighbours
+constexpr int UFC_NODES = UFC_CELLS * 8;
+constexpr int UFC_BRUTE_TESTS = 4096;  // brute-force sweep only while (own points) x (neighbourhood points) stays below this
+struct __align__(16) UfcWarpSmem {
+    float4 tile[UFC_TILE_PTS];
+    int cstart[16];            // first sorted point of cell c
+    int coff[16];              // position of cell c's first point in the tile; coff[14] = coff[15] = total
+    int ffirst[16];            // first fine id of cell c
+    int ownb[12];              // tile position of the first point of A's child j; ownb[n_a] = n_own
+    unsigned char attach[UFC_NODES];  // for neighbour node x = c*8 + j: an own child adjacent to it (0xff = none)
+    uint64_t bar;
+};
+
+// Sparse tasks.  One warp per occupied coarse cell A (half stencil: cell 0 = A, cells 1..13 = the neighbours that
+// follow A in (z, y, x) order, so every unordered pair of adjacent coarse cells belongs to exactly one warp).
+// The forward neighbourhood (<= UFC_TILE_PTS points, the normal case on LiDAR frames) is staged in shared memory
+// with TMA bulk copies, one per occupied cell.  Each lane keeps one staged point q in registers and the warp sweeps
+// A's own points child by child through broadcast LDS.128: every (p_i, q) pair gets the exact fp32 predicate and a
+// lane remembers WHICH of A's children hit it -- no branches inside the sweep, rings 1 and 2 covered at once.
+// Lanes are grouped by fine cell (match.any on the fine id), one ballot per child turns lane hits into
+// (child a, fine cell b) adjacencies.  The connected components among A's <= 8 children are tracked in a packed
+// warp-uniform register (8 x 8-bit masks), every adjacent neighbour cell remembers one child it touches, and at the
+// end ONE global edge per touched fine cell goes into the lock-free union-find (atomicMin hooking).
+// Tasks whose neighbourhood is too large for the tile are appended to the dense list for k_uf_dense.
+__global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restrict__ spts, const int* __restrict__ fc_start,
+                                                            const int4* __restrict__ crec, const int* __restrict__ nbr,
+                                                            int* __restrict__ d_counts, int* parent, float r2, int use_tma,
+                                                            int* __restrict__ dense_list, int dense_cap) {
+    extern __shared__ __align__(16) unsigned char ufc_smem_raw[];
+    UfcWarpSmem& sm = reinterpret_cast<UfcWarpSmem*>(ufc_smem_raw)[warp_id()];
+    const int lane = lane_id();
+    const int n_tasks = d_counts[CNT_COARSE];
+    const int n_warps = gridDim.x * UFC_WARPS;
+    if (lane == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+    // software pipeline of the lookup chain: neighbour ids are fetched two tasks ahead, records one task ahead
+    const int first = blockIdx.x * UFC_WARPS + warp_id();
+    int nci_1 = -1, nci_2 = -1;
+    int4 rec_1 = make_int4(0, 0, 0, 0);
+    if (lane < 16) {
+        if (first < n_tasks) nci_1 = __ldg(nbr + first * 16 + lane);
+        if (first + n_warps < n_tasks) nci_2 = __ldg(nbr + (first + n_warps) * 16 + lane);
+    }
+    if (nci_1 >= 0) rec_1 = __ldg(crec + nci_1);
+
+    for (int ci = first; ci < n_tasks; ci += n_warps) {
+        const int4 rec = rec_1;
+        rec_1 = make_int4(0, 0, 0, 0);
+        if (nci_2 >= 0) rec_1 = __ldg(crec + nci_2);       // record of the next task (consumed next iteration)
+        nci_2 = -1;
+        if (lane < 16 && ci + 2 * n_warps < n_tasks) nci_2 = __ldg(nbr + (ci + 2 * n_warps) * 16 + lane);
+        const int incl = warp_inclusive_scan(rec.y);
+        const int ptot = __shfl_sync(kFull, incl, 31);
+        const int n_own = __shfl_sync(kFull, rec.y, 0);
+        const int own0 = __shfl_sync(kFull, rec.x, 0);
+        const int ffirst0 = __shfl_sync(kFull, rec.z, 0);
+        const int n_a = __popc((unsigned)__shfl_sync(kFull, rec.w, 0));
+        if (!(ptot <= UFC_TILE_PTS && n_own * ptot <= UFC_BRUTE_TESTS)) {
+            // dense neighbourhood: hand the task to k_uf_dense
+            if (lane == 0) {
+                const int slot = atomicAdd(&d_counts[CNT_DENSE], 1);
+                if (slot < dense_cap) dense_list[slot] = ci;
+                else atomicOr(&d_counts[CNT_FLAGS], 1);  // cannot happen (see dense_cap); the host reports it
+            }
+            continue;
+        }
+        if (lane < 16) {
+            sm.cstart[lane] = rec.x;
+            sm.coff[lane] = incl - rec.y;  // lanes >= 14 hold ptot
+            sm.ffirst[lane] = rec.z;
+        }
+        if (lane <= n_a) sm.ownb[lane] = __ldg(fc_start + ffirst0 + lane) - own0;
+        for (int x = lane; x < UFC_NODES / 4; x += 32) reinterpret_cast<uint32_t*>(sm.attach)[x] = 0xffffffffu;
+        // ---- stage the forward neighbourhood: TMA bulk copies (one per occupied cell), or plain loads ----
+        bool staged = false;
+        if (use_tma & 1) {
+            if (lane == 0) mbar_arrive_expect_tx(&sm.bar, (uint32_t)ptot * 16u);
+            __syncwarp();
+            if (rec.y > 0) tma_load_1d(&sm.tile[incl - rec.y], spts + rec.x, (uint32_t)rec.y * 16u, &sm.bar);
+            const bool ok = mbar_wait_bounded(&sm.bar, parity);
+            parity ^= 1u;
+            staged = __all_sync(kFull, ok);
+        }
+        __syncwarp();
+        if (!staged) {
+            for (int t = lane; t < ptot; t += 32) {
+                int c = 0;
+#pragma unroll
+                for (int k = 8; k > 0; k >>= 1)
+                    if (c + k < UFC_CELLS && sm.coff[c + k] <= t) c += k;
+                sm.tile[t] = __ldg(spts + sm.cstart[c] + (t - sm.coff[c]));
+            }
+            __syncwarp();
+        }
+
+        // ---- sweep ----
+        unsigned long long comp = 0x8040201008040201ull;  // byte a = mask of A's children connected to child a (warp uniform)
+        for (int t0 = 0; t0 < ptot; t0 += 32) {
+            const int t = t0 + lane;
+            const bool valid = t < ptot;
+            int c = 0, fid = -1 - lane;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+#pragma unroll
+                for (int k = 8; k > 0; k >>= 1)
+                    if (c + k < UFC_CELLS && sm.coff[c + k] <= t) c += k;
+                q = sm.tile[t];
+                fid = __float_as_int(q.w);                    // k_cells_write stores the fine cell id in .w
+            }
+            unsigned hit = 0;  // bit a: some point of A's child a is within tol of q
+            for (int a = 0; a < n_a; ++a) {
+                const int i1 = sm.ownb[a + 1];
+                bool pred = false;
+                for (int i = sm.ownb[a]; i < i1; ++i) {
+                    const float4 pi = sm.tile[i];
+                    pred |= dist2_exact(pi.x, pi.y, pi.z, q.x, q.y, q.z) < r2;
+                }
+                hit |= (unsigned)pred << a;
+            }
+            if (!valid) hit = 0;
+            const int j = fid - sm.ffirst[c];                 // child index of q's fine cell inside its coarse cell
+            if (valid && c == 0) hit &= (1u << j) - 1u;       // inside A each unordered child pair once (a < j)
+            const unsigned peers = __match_any_sync(kFull, fid);
+            unsigned hm = 0;
+            for (int a = 0; a < n_a; ++a) {
+                const unsigned bal = __ballot_sync(kFull, (hit >> a) & 1u);
+                if (bal & peers) hm |= 1u << a;
+            }
+            const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
+            if (!leader) hm = 0;
+            if (leader) {
+                if (c == 0) hm |= 1u << j;                    // an own child: it joins the children it touches
+                else sm.attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
+            }
+            // children that this fine cell links for the first time -> merge their components (at most n_a - 1 merges
+            // per task; the need is re-evaluated after every merge so duplicates in the same chunk cost nothing)
+            for (;;) {
+                const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
+                const unsigned bm = __ballot_sync(kFull, (hm & ~lowc) != 0u);
+                if (!bm) break;
+                const unsigned m = __shfl_sync(kFull, hm, __ffs(bm) - 1);
+                unsigned nc = 0;
+                for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
+                for (unsigned mm = nc; mm; mm &= mm - 1) {
+                    const int sh = 8 * (__ffs(mm) - 1);
+                    comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- one global edge per touched fine cell.  The walks up the global forest are latency bound, so a lane
+        // first issues the level-1 and level-2 parent loads of all its (<= 5) edges back to back and only then hooks.
+        int ea[5], eb[5];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int x = lane + 32 * r;
+            ea[r] = -1; eb[r] = -1;
+            if (x < UFC_NODES) {
+                const unsigned a = sm.attach[x];
+                if (a != 0xffu) {
+                    ea[r] = sm.ffirst[x >> 3] + (x & 7);
+                    eb[r] = ffirst0 + __ffs((unsigned)((comp >> (8 * a)) & 0xffull)) - 1;
+                }
+            }
+        }
+        ea[4] = -1; eb[4] = -1;
+        if (lane < n_a) {
+            const int rootc = __ffs((unsigned)((comp >> (8 * lane)) & 0xffull)) - 1;
+            if (rootc != lane) { ea[4] = ffirst0 + lane; eb[4] = ffirst0 + rootc; }
+        }
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+            if (ea[r] >= 0) { ea[r] = ld_cg(parent + ea[r]); eb[r] = ld_cg(parent + eb[r]); }
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+            if (ea[r] >= 0) { ea[r] = ld_cg(parent + ea[r]); eb[r] = ld_cg(parent + eb[r]); }
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+            if (ea[r] >= 0 && ea[r] != eb[r]) uf_unite(parent, ea[r], eb[r]);  // ancestors stand in for the cells themselves
+        __syncwarp();
+    }
+}
+
+// Dense tasks (listed by k_uf_sparse).  RING 1: fine-cell pairs at Chebyshev distance <= 1; RING 2 (second launch,
+// after a global compress): distance 2.  A pair whose cells already share a global root is skipped without touching
+// a point -- on a densely sampled surface a ring-2 pair is always connected through the ring-1 cell between them --
+// otherwise the warp searches cooperatively for ONE witness pair (dense neighbours produce it in the first 32x32
+// block) and hooks the two cells in the global union-find.
+template <int RING>
+__global__ void __launch_bounds__(UFC_THREADS) k_uf_dense(const float4* __restrict__ spts, const int* __restrict__ fc_start,
+                                                           const int4* __restrict__ crec, const int* __restrict__ nbr,
+                                                           const int* __restrict__ d_counts, int* parent, float r2,
+                                                           const int* __restrict__ dense_list, int dense_cap) {
+    __shared__ int s_ffirst[UFC_WARPS][16];
+    __shared__ int s_cmask[UFC_WARPS][16];
+    const int lane = lane_id(), w = warp_id();
+    const int n_tasks = min(d_counts[CNT_DENSE], dense_cap);
+    const int n_warps = gridDim.x * UFC_WARPS;
+    // one warp per (dense task, child a of its coarse cell): 8x more parallelism than a warp per task
+    for (int work = blockIdx.x * UFC_WARPS + w; work < n_tasks * 8; work += n_warps) {
+        const int task = work >> 3, a = work & 7;
+        int nci = -1;
+        if (lane < UFC_CELLS) nci = __ldg(nbr + dense_list[task] * 16 + lane);
+        int4 rec = make_int4(0, 0, 0, 0);
+        if (nci >= 0) rec = __ldg(crec + nci);
+        __syncwarp();
+        if (lane < 16) {
+            s_ffirst[w][lane] = rec.z;
+            s_cmask[w][lane] = rec.w;
+        }
+        __syncwarp();
+        const unsigned mask0 = (unsigned)s_cmask[w][0];
+        const int n_a = __popc(mask0);
+        if (a < n_a) {
+            const int fid_a = s_ffirst[w][0] + a;
+            const int a0 = __ldg(fc_start + fid_a), a1 = __ldg(fc_start + fid_a + 1);
+            const int code_a = __fns(mask0, 0, a + 1);
+            const int ax = code_a & 1, ay = (code_a >> 1) & 1, az = code_a >> 2;
+            for (int nb0 = 0; nb0 < UFC_NODES; nb0 += 32) {
+                const int node = nb0 + lane;
+                const int c = node >> 3, j = node & 7;
+                bool elig = false;
+                if (c < UFC_CELLS && j < __popc((unsigned)s_cmask[w][c]) && (c > 0 || j > a)) {
+                    const int cs = 13 + c;
+                    const int code_b = __fns((unsigned)s_cmask[w][c], 0, j + 1);
+                    const int bx = 2 * ((cs % 3) - 1) + (code_b & 1), by = 2 * (((cs / 3) % 3) - 1) + ((code_b >> 1) & 1),
+                              bz = 2 * ((cs / 9) - 1) + (code_b >> 2);
+                    const int ring = max(max(abs(bx - ax), abs(by - ay)), abs(bz - az));
+                    elig = (RING == 1 ? ring <= 1 : ring == 2) && uf_find(parent, s_ffirst[w][c] + j) != uf_find(parent, fid_a);
+                }
+                unsigned bm = __ballot_sync(kFull, elig);
+                while (bm) {
+                    const int sl = __ffs(bm) - 1;
+                    bm &= bm - 1;
+                    const int nd = nb0 + sl;
+                    const int fid_b = s_ffirst[w][nd >> 3] + (nd & 7);
+                    int same = 0;
+                    if (lane == 0) same = uf_find(parent, fid_b) == uf_find(parent, fid_a);
+                    same = __shfl_sync(kFull, same, 0);
+                    if (same) continue;
+                    const int b0 = __ldg(fc_start + fid_b), b1 = __ldg(fc_start + fid_b + 1);
+                    const bool found = coop_witness(spts, a0, a1, b0, b1, r2);
+                    if (found && lane == 0) uf_unite(parent, fid_a, fid_b);
+                    __syncwarp();
+                }
+            }
+        }
     }
 }
 

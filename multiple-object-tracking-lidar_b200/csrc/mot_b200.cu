@@ -18,6 +18,7 @@
 //   K9  k_ihgp_step                   batched track filter (separate entry point)
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,16 +39,16 @@ static_assert(sizeof(mot_cluster_stat) == 40, "stat layout");
 // kernel ids for the launch counter / per-kernel profile (mot_profile_read)
 enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_CELLS_WRITE,
-    KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
+    KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
-    "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_comp_accumulate", "k_kept_list",
+    "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_comp_accumulate", "k_kept_list",
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
-    "k_cluster_stats", "k_farthest_pair", "k_circumcentre", "k_ihgp_step"};
+    "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step"};
 
 struct mot_handle {
     int device = 0;
@@ -70,7 +71,7 @@ struct mot_handle {
     float4 *d_in = nullptr, *d_pts = nullptr, *d_spts = nullptr;
     void* d_keys[2] = {nullptr, nullptr};  // 8 bytes per point each (u32 or u64 keys)
     uint32_t* d_vals[2] = {nullptr, nullptr};
-    int *d_fc_start = nullptr, *d_cc_first = nullptr, *d_pcell = nullptr, *d_parent = nullptr, *d_root = nullptr;
+    int *d_fc_start = nullptr, *d_cc_first = nullptr, *d_parent = nullptr, *d_root = nullptr;
     int *d_csize = nullptr, *d_cmin = nullptr, *d_crank = nullptr, *d_labels = nullptr;
     void* d_hkeys = nullptr;
     int* d_hvals = nullptr;
@@ -86,6 +87,13 @@ struct mot_handle {
     int* d_frame_cl_offsets = nullptr;
     size_t frame_capacity = 0;
     ClusterStat* d_stats = nullptr;
+    StatAcc* d_statacc = nullptr;
+    int4* d_crec = nullptr;
+    int* d_dense_list = nullptr;
+    int* d_nbr = nullptr;
+    int dense_cap = 0;
+    int uf_mode = 1;   // 1: coarse-cell warps + TMA staging + local union-find (default); 0: v1 two-phase fine-cell warps
+    int uf_tma = 1;
     float4* d_centroids = nullptr;
     PairCand* d_cands = nullptr;
     size_t table_capacity = 0, cand_capacity = 0;
@@ -108,6 +116,7 @@ struct mot_handle {
     const float4* res_cloud = nullptr;  // the clustered cloud on the device (d_pts or the caller's pointer)
     int res_M = 0, res_K = 0, res_total = 0, res_idx_buf = 0, res_frames = 1;
     int res_fine = 0, res_coarse = 0, res_key_bits = 0;
+    int sorted_buf = 0;
     bool res_centroids = false;
     Prof prof;
     float prof_ms[KID_N] = {};
@@ -155,8 +164,10 @@ int ensure_tables(mot_handle* h, size_t K, size_t cands) {
         size_t cap = K + K / 2 + 1024;
         if (h->d_stats) cudaFree(h->d_stats);
         if (h->d_centroids) cudaFree(h->d_centroids);
-        h->d_stats = nullptr; h->d_centroids = nullptr;
+        if (h->d_statacc) cudaFree(h->d_statacc);
+        h->d_stats = nullptr; h->d_centroids = nullptr; h->d_statacc = nullptr;
         CK(dalloc(&h->d_stats, cap));
+        CK(dalloc(&h->d_statacc, cap));
         CK(dalloc(&h->d_centroids, cap));
         h->table_capacity = cap;
     }
@@ -206,6 +217,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, h->prof, KID_SORT_HIST);
     const KT* skeys = keys[sb];
     const uint32_t* svals = h->d_vals[sb];
+    h->sorted_buf = sb;
 
     // coarse-cell hash sized for at most min(M, #coarse cells) entries at load factor <= 0.5
     long long coarse_cap = (long long)g.ncx * g.ncy * g.ncz * n_frames;
@@ -219,9 +231,9 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     const int hshift = 32 - hb;
 
     const Chunking ck = make_chunking(M, CELL_THREADS, CELL_MAX_GRID);
-    LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk));
-    LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, M, ck.chunk, h->d_blk, h->d_fc_start, h->d_cc_first,
-                                                                               h->d_pcell, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
+    LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, M, ck.chunk, h->d_blk));
+    LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
+                                                                               h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
                                                                                h->d_counts));
     CK(cudaEventRecord(h->ev[2], st));
@@ -231,14 +243,34 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (uf_grid > h->num_sms * 8) uf_grid = h->num_sms * 8;
     int flat_grid = (M + 255) / 256;
     if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
-    LAUNCH(KID_UF1, k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
-                                                                      reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                      h->d_counts, h->d_parent, g, r2));
-    LAUNCH(KID_FLATTEN1, k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
-    LAUNCH(KID_UF2, k_uf_pairs<KT, 2><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
-                                                                      reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                      h->d_counts, h->d_parent, g, r2));
-    LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+    if (h->uf_mode == 1) {
+        int rgrid = (M + 15) / 16;
+        if (rgrid > h->num_sms * 8) rgrid = h->num_sms * 8;
+        LAUNCH(KID_COARSE_REC, k_coarse_records<KT><<<rgrid, 256, 0, st>>>(skeys, h->d_fc_start, h->d_cc_first, h->d_counts,
+                                                                           reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift, g,
+                                                                           h->d_crec, h->d_nbr));
+        int cgrid = (M + UFC_WARPS - 1) / UFC_WARPS;
+        if (cgrid > h->num_sms * 5) cgrid = h->num_sms * 5;
+        const size_t usm = UFC_WARPS * sizeof(UfcWarpSmem);
+        LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
+                                                                           h->uf_tma, h->d_dense_list, h->dense_cap));
+        int dgrid = cgrid < h->num_sms * 4 ? cgrid : h->num_sms * 4;
+        LAUNCH(KID_UF_DENSE1, k_uf_dense<1><<<dgrid, UFC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
+                                                                            h->d_dense_list, h->dense_cap));
+        LAUNCH(KID_FLATTEN1, k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+        LAUNCH(KID_UF_DENSE, k_uf_dense<2><<<dgrid, UFC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
+                                                                           h->d_dense_list, h->dense_cap));
+        LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+    } else {
+        LAUNCH(KID_UF1, k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
+                                                                          reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
+                                                                          h->d_counts, h->d_parent, g, r2));
+        LAUNCH(KID_FLATTEN1, k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+        LAUNCH(KID_UF2, k_uf_pairs<KT, 2><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
+                                                                          reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
+                                                                          h->d_counts, h->d_parent, g, r2));
+        LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+    }
     CK(cudaEventRecord(h->ev[3], st));
     CK(cudaGetLastError());
     return MOT_OK;
@@ -322,6 +354,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     const int total = h->h_pinned[8 + CNT_TOTAL];
     h->res_K = K;
     h->res_total = total;
+    if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
     h->res_fine = h->h_pinned[8 + CNT_FINE];
     h->res_coarse = h->h_pinned[8 + CNT_COARSE];
     h->res_key_bits = total_bits;
@@ -345,7 +378,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     }
     // ---- CSR emission: stable partition of 0..M-1 by cluster rank ----
     uint32_t* pk[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
-    LAUNCH(KID_POINT_RANK, k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_pcell, h->d_root, h->d_crank, h->d_cmin, M, K, pk[0],
+    LAUNCH(KID_POINT_RANK, k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_vals[h->sorted_buf], h->d_root, h->d_crank, h->d_cmin, M, K, pk[0],
                                                                         h->d_labels));
     h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, h->prof, KID_PART_HIST);
     if (n_frames > 1 && total > 0) {
@@ -364,7 +397,11 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         rc = ensure_tables(h, (size_t)K, with_centroids ? (size_t)K * slabs : 0);
         if (rc != MOT_OK) return rc;
         int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
-        LAUNCH(KID_STATS, k_cluster_stats<<<sgrid, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, h->d_stats));
+        LAUNCH(KID_STATS_INIT, k_stats_init<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, K));
+        const int per_block = 32 * STAT_GROUPS_PER_WARP * (STAT_THREADS / 32);
+        LAUNCH(KID_STATS, k_stats_accumulate<<<(total + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf],
+                                                                                                         K, total, h->d_statacc));
+        LAUNCH(KID_STATS_FIN, k_stats_finalize<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, h->d_cl_offsets, K, h->d_stats));
         if (with_centroids) {
             LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
                                                                                        h->d_cands));
@@ -505,7 +542,6 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         }
         CK(dalloc(&h->d_fc_start, n + 1));
         CK(dalloc(&h->d_cc_first, n + 1));
-        CK(dalloc(&h->d_pcell, n));
         CK(dalloc(&h->d_parent, n));
         CK(dalloc(&h->d_root, n));
         CK(dalloc(&h->d_csize, n));
@@ -513,6 +549,10 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_crank, n));
         CK(dalloc(&h->d_labels, n));
         CK(dalloc(&h->d_cl_offsets, n + 1));
+        CK(dalloc(&h->d_crec, n));
+        h->dense_cap = (int)(n / 4 + 1024);  // a dense task's forward neighbourhood holds >= 64 points and a point lies in <= 14 of them
+        CK(dalloc(&h->d_dense_list, (size_t)h->dense_cap));
+        CK(dalloc(&h->d_nbr, n * 16));
         int hb = ceil_log2(2 * (long long)n);
         if (hb < 4) hb = 4;
         h->hash_capacity = (size_t)1 << hb;
@@ -532,6 +572,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         for (auto& e : h->ev) CK(cudaEventCreate(&e));
         for (auto& e : h->timer_ev) CK(cudaEventCreate(&e));
         h->prof.st = h->stream;
+        CK(cudaFuncSetAttribute(k_uf_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(UFC_WARPS * sizeof(UfcWarpSmem))));
+        if (const char* e = getenv("MOT_UF_MODE")) h->uf_mode = atoi(e);
+        if (const char* e = getenv("MOT_UF_TMA")) h->uf_tma = atoi(e);
         CK(rs_configure<uint32_t>());
         CK(rs_configure<uint64_t>());
         CK(cudaFuncSetAttribute(k_clusters_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMALL_SMEM));
@@ -558,9 +601,9 @@ int mot_destroy(mot_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_in, h->d_pts, h->d_spts, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_ckeys[0], h->d_ckeys[1],
-                    h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_pcell, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
+                    h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
                     h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->d_blk,
-                    h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_centroids, h->d_cands, h->d_bits,
+                    h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -32,36 +32,54 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const KT* __restrict__ k
     const int begin = blockIdx.x * chunk;
     const int end = min(n, begin + chunk);
     const int lane = lane_id();
-    for (int base = begin; base < end; base += RS_THREADS) {
-        const int i = base + threadIdx.x;
-        const bool valid = i < end;
-        const unsigned d = valid ? (unsigned)((keys[i] >> shift) & mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(kFull, d);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh_hist[d], (unsigned)__popc(peers));
+    // RS_ITEMS coalesced loads in flight per thread, then warp-aggregated shared-memory atomics
+    for (int base = begin; base < end; base += RS_TILE) {
+        KT k[RS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            k[j] = i < end ? keys[i] : (KT)0;
+        }
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            const bool valid = i < end;
+            const unsigned d = valid ? (unsigned)((k[j] >> shift) & mask) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(kFull, d);
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh_hist[d], (unsigned)__popc(peers));
+        }
     }
     __syncthreads();
     for (int d = threadIdx.x; d < R; d += RS_THREADS) hist[(size_t)d * gridDim.x + blockIdx.x] = sh_hist[d];
 }
 
-// One warp per digit: prefix[d][b] = sum_{b' < b} hist[d][b'], tot[d] = sum_b hist[d][b].
+// One warp per digit: prefix[d][b] = sum_{b' < b} hist[d][b'], tot[d] = sum_b hist[d][b].  The whole row
+// (G <= RS_MAX_GRID counters) is loaded coalesced up front, then scanned 32 counters at a time.
+constexpr int RS_SCAN_CHUNKS = (RS_MAX_GRID + 31) / 32;
 __global__ void __launch_bounds__(256) k_rs_scan(const unsigned* __restrict__ hist, unsigned* __restrict__ prefix,
                                                   unsigned* __restrict__ tot, int R, int G) {
     const int d = blockIdx.x * 8 + warp_id();
     if (d >= R) return;
     const int lane = lane_id();
-    const int per = (G + 31) / 32;
-    const int s = lane * per, e = min(G, s + per);
     const unsigned* row = hist + (size_t)d * G;
     unsigned* prow = prefix + (size_t)d * G;
-    int local = 0;
-    for (int i = s; i < e; ++i) local += (int)row[i];
-    const int incl = warp_inclusive_scan(local);
-    int run = incl - local;
-    for (int i = s; i < e; ++i) {
-        prow[i] = (unsigned)run;
-        run += (int)row[i];
+    int v[RS_SCAN_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < RS_SCAN_CHUNKS; ++c) {
+        const int i = c * 32 + lane;
+        v[c] = i < G ? (int)row[i] : 0;
     }
-    if (lane == 31) tot[d] = (unsigned)incl;
+    int carry = 0;
+#pragma unroll
+    for (int c = 0; c < RS_SCAN_CHUNKS; ++c) {
+        const int i = c * 32 + lane;
+        if (c * 32 < G) {
+            const int incl = warp_inclusive_scan(v[c]);
+            if (i < G) prow[i] = (unsigned)(carry + incl - v[c]);
+            carry += __shfl_sync(kFull, incl, 31);
+        }
+    }
+    if (lane == 0) tot[d] = (unsigned)carry;
 }
 
 constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes) {

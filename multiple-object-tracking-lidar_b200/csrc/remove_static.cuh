@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(RSK_THREADS) k_rs_count(const float4* __restri
             mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
             mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
         }
-    if (lane_id() == 0 && cnt >= 0) {
+    if (lane_id() == 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             atomicMin(&sbox[d], float_to_ordered(mn[d]));
@@ -169,13 +169,26 @@ __global__ void __launch_bounds__(RSK_THREADS) k_rs_compact(const float4* __rest
     }
 }
 
-// Bounding box + finiteness of an already compacted cloud (mot_cluster without removeStatic).
+// Bounding box + finiteness of an already compacted cloud (mot_cluster without removeStatic).  Two points per
+// thread and iteration in flight, block-level reduction in shared memory, six global atomics per block.
 __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, int n, int* __restrict__ bbox) {
+    __shared__ float sred[6][8];
+    __shared__ int sbad;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     bool bad = false;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (threadIdx.x == 0) sbad = 0;
+    const int stride = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        const float4 p = ld_stream(pts + i), q = ld_stream(pts + i + stride);
+        bad |= !(fabsf(p.x) < INFINITY) || !(fabsf(p.y) < INFINITY) || !(fabsf(p.z) < INFINITY);
+        bad |= !(fabsf(q.x) < INFINITY) || !(fabsf(q.y) < INFINITY) || !(fabsf(q.z) < INFINITY);
+        mn[0] = fminf(mn[0], fminf(p.x, q.x)); mn[1] = fminf(mn[1], fminf(p.y, q.y)); mn[2] = fminf(mn[2], fminf(p.z, q.z));
+        mx[0] = fmaxf(mx[0], fmaxf(p.x, q.x)); mx[1] = fmaxf(mx[1], fmaxf(p.y, q.y)); mx[2] = fmaxf(mx[2], fmaxf(p.z, q.z));
+    }
+    if (i < n) {
         const float4 p = ld_stream(pts + i);
-        if (!(fabsf(p.x) < INFINITY) || !(fabsf(p.y) < INFINITY) || !(fabsf(p.z) < INFINITY)) bad = true;
+        bad |= !(fabsf(p.x) < INFINITY) || !(fabsf(p.y) < INFINITY) || !(fabsf(p.z) < INFINITY);
         mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
         mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
     }
@@ -186,14 +199,21 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, in
             mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
             mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
         }
+    __syncthreads();
     if (lane_id() == 0) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            atomicMin(&bbox[d], float_to_ordered(mn[d]));
-            atomicMax(&bbox[3 + d], float_to_ordered(mx[d]));
-        }
+        for (int d = 0; d < 3; ++d) { sred[d][warp_id()] = mn[d]; sred[3 + d][warp_id()] = mx[d]; }
     }
-    if (__any_sync(kFull, bad) && lane_id() == 0) atomicOr(&bbox[6], 1);
+    if (__any_sync(kFull, bad) && lane_id() == 0) atomicOr(&sbad, 1);
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int d = threadIdx.x;
+        float v = sred[d][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = d < 3 ? fminf(v, sred[d][w]) : fmaxf(v, sred[d][w]);
+        if (d < 3) atomicMin(&bbox[d], float_to_ordered(v));
+        else atomicMax(&bbox[d], float_to_ordered(v));
+    }
+    if (threadIdx.x == 0 && sbad) atomicOr(&bbox[6], 1);
 }
 
 }  // namespace mot
