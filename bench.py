@@ -100,21 +100,24 @@ def kernel_bytes(name, M, cf, cc, K, total, key_bytes, n_sort_passes, R_G=1024 *
     table = {
         "k_bbox": 16 * M,
         "k_cell_keys": (16 + kb) * M,
-        "k_rs_hist[cells]": kb * M,
-        "k_rs_scatter[cells]": 2 * (kb + 4) * M,          # read pair + write pair (first pass synthesises the index)
-        "k_cells_count": (kb + 4 + 16 + 16) * M,          # key, index, gather point, write sorted SoA point
-        "k_cells_write": (kb + 4) * M + 24 * cf + 16 * cc,  # key, cell id per point, cell tables + hash insert
-        "k_uf_pairs<1>": 16 * M + 16 * cf + 12 * cc,      # every sorted point once + cell table + parent + hash
-        "k_uf_pairs<2>": 16 * cf + 12 * cc,               # cell-level only unless a witness search is needed
+        "k_rs_hist[cells]": kb * M,                       # onesweep: one read of the keys for every pass's histogram
+        "k_rs_scatter[cells]": 2 * (kb + 4) * M,          # one onesweep pass: read pair + write pair
+        "k_cells_count": kb * M,
+        "k_cells_write": (kb + 4 + 16 + 16) * M + 24 * cf + 16 * cc,  # key, index, gather point, write sorted SoA point, tables
+        "k_coarse_records": 12 * cf + 80 * cc,            # record (16 B) + neighbour row (64 B) per coarse cell
+        "k_uf_sparse": 16 * M + 80 * cc + 8 * cf,         # every sorted point once + record/neighbour row + parent r/w
         "k_uf_flatten<in-place>": 8 * cf,
         "k_uf_flatten<root>": 8 * cf,
         "k_comp_accumulate": 16 * cf,
         "k_kept_list": 12 * cf + 12 * K,
         "k_clusters_small": 24 * K,
-        "k_point_rank": (16 + 4 + 4 + 4) * M,             # sorted point (index in .w), cell id, key out, label out
+        "k_point_rank": (16 + 4 + 4 + 4) * M,             # sorted point (cell id in .w), index, key out, label out
         "k_rs_hist[csr]": 4 * M,
         "k_rs_scatter[csr]": 16 * M,
-        "k_cluster_stats": 20 * total + 40 * K,
+        "k_stats_accumulate": 20 * total + 48 * K,
+        # v1 kernels (MOT_UF_MODE=0)
+        "k_uf_pairs<1>": 16 * M + 16 * cf + 12 * cc,
+        "k_uf_pairs<2>": 16 * cf + 12 * cc,
     }
     return table.get(name)
 
@@ -139,26 +142,24 @@ def run_b200(args, rank, world, local_rank):
     F = args.frames
     frames_np = [scene.frame(rank * F + f) for f in range(F)]
     n_pts = len(frames_np[0])
-    d_frames = [torch.from_numpy(fr).to(dev) for fr in frames_np]
-    trk = mot.Tracker(device=local_rank, max_points=n_pts, max_tracks=0)
+    all_np = np.ascontiguousarray(np.concatenate(frames_np))
+    frame_offsets = np.arange(F + 1, dtype=np.int64) * n_pts
+    d_all = torch.from_numpy(all_np).to(dev)          # the step's frames, resident in HBM
+    trk = mot.Tracker(device=local_rank, max_points=F * n_pts, max_tracks=0)
     trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
-
-    table_buf = torch.zeros((F, 4096, 10), dtype=torch.float32, device=dev)
+    table_buf = torch.zeros((1 << 16, 10), dtype=torch.float32, device=dev)
 
     def step_device(gather):
-        launches, counts = 0, []
-        for f in range(F):
-            trk.frame_device(d_frames[f].data_ptr(), n_pts)
-            launches += trk.last_launches()
-            if gather:
-                M, K, total = trk.result_counts()
-                k = min(K, table_buf.shape[1])
-                trk.lib.mot_result_fetch(trk.h, None, 0, None, 0, None, 0, table_buf[f].data_ptr(), None, k) if k else None
-                counts.append(k)
+        """One pass of the hot path over the step's batch of F frames (frame id rides in the voxel key)."""
+        trk.cluster_batch_device(d_all.data_ptr(), frame_offsets)
+        launches = trk.last_launches()
         if gather:
-            cnt = torch.tensor(counts, dtype=torch.int64, device=dev)
-            payload = torch.cat([table_buf[f, :counts[f]] for f in range(F)]) if sum(counts) else torch.zeros((0, 10), device=dev)
-            shard.gather_tables(cnt, payload, device=dev)
+            M, K, total = trk.result_counts()
+            k = min(K, table_buf.shape[0])
+            if k:
+                trk.lib.mot_result_fetch(trk.h, None, 0, None, 0, None, 0, table_buf.data_ptr(), None, k)
+            cnt = torch.tensor([k], dtype=torch.int64, device=dev)
+            shard.gather_tables(cnt, table_buf[:k], device=dev)
         return launches
 
     gather = world > 1
@@ -179,7 +180,6 @@ def run_b200(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     if dist:
         dist.barrier()
-    clocks = sampler.stop()
     t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -187,26 +187,25 @@ def run_b200(args, rank, world, local_rank):
     pts_per_step = world * F * n_pts
     value = pts_per_step * args.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- e2e: host buffers through mot_cluster (pinned), copies inside the timed region ----
-    h_frames = [torch.from_numpy(fr).pin_memory() for fr in frames_np]
-    h_off = torch.empty(n_pts + 1, dtype=torch.int32).pin_memory()
-    h_idx = torch.empty(n_pts, dtype=torch.int32).pin_memory()
+    # ---- e2e: host buffers through mot_cluster_batch (pinned), copies inside the timed region ----
     import ctypes as C
+    h_all = torch.from_numpy(all_np).pin_memory()
+    h_fco = torch.empty(F + 1, dtype=torch.int32).pin_memory()
+    h_off = torch.empty(F * n_pts + 1, dtype=torch.int32).pin_memory()
+    h_idx = torch.empty(F * n_pts, dtype=torch.int32).pin_memory()
     kk = C.c_int32(0)
 
     def step_e2e():
-        d2h = 0
-        for f in range(F):
-            rc = trk.lib.mot_cluster(trk.h, h_frames[f].data_ptr(), n_pts, h_off.data_ptr(), n_pts + 1, h_idx.data_ptr(), n_pts, C.byref(kk))
-            assert rc == 0, trk.lib.mot_last_error(trk.h)
-            d2h += 4 * (kk.value + 1) + 4 * int(h_off[kk.value])
-        return d2h
+        rc = trk.lib.mot_cluster_batch(trk.h, h_all.data_ptr(), frame_offsets, F, h_fco.data_ptr(), h_off.data_ptr(), F * n_pts + 1,
+                                       h_idx.data_ptr(), F * n_pts, C.byref(kk))
+        assert rc == 0, trk.lib.mot_last_error(trk.h)
+        return 4 * (F + 1) + 4 * (kk.value + 1) + 4 * int(h_off[kk.value])
 
     for _ in range(3):
         step_e2e()
     if dist:
         dist.barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     trk.timer_start()
     d2h_bytes = 0
     for _ in range(e2e_steps):
@@ -218,6 +217,18 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pts_per_step * e2e_steps / (float(te[0]) * 1e-3) / 1e6
 
+    # ---- single-frame latency (one 2^20-point frame per call, as the reference's callback sees it) ----
+    lat = []
+    for f in range(F):
+        trk.frame_device(d_all[f * n_pts:(f + 1) * n_pts].data_ptr(), n_pts)
+    for rep in range(3):
+        for f in range(F):
+            trk.timer_start()
+            trk.frame_device(d_all[f * n_pts:(f + 1) * n_pts].data_ptr(), n_pts)
+            lat.append(trk.timer_stop())
+    single_frame_us = float(np.median(lat)) * 1e3
+    clocks = sampler.stop()
+
     # ---- per-kernel attribution (separate pass with event pairs around every launch) ----
     trk.set_profiling(True)
     prof_steps = 3
@@ -225,6 +236,7 @@ def run_b200(args, rank, world, local_rank):
         step_device(False)
     prof = trk.profile()
     trk.set_profiling(False)
+    F_prof = 1  # kernel figures are per launch over the whole batch
     M, K, total = trk.result_counts()
     grid = trk.result_grid()
     key_bytes = 4 if grid["key_bits"] <= 32 else 8
@@ -234,7 +246,7 @@ def run_b200(args, rank, world, local_rank):
     for name, (tms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         avg_ms = tms / cnt
         b = kernel_bytes(name, M, grid["fine_cells"], grid["coarse_cells"], K, total, key_bytes, 0)
-        kernels.append({"kernel": name, "launches_per_frame": cnt / (prof_steps * F), "avg_us": round(avg_ms * 1e3, 2),
+        kernels.append({"kernel": name, "launches_per_step": cnt / prof_steps, "avg_us": round(avg_ms * 1e3, 2),
                         "share": round(tms / tot_kernel_ms, 4), "alg_bytes": b,
                         "gbs": round(b / (avg_ms * 1e-3) / 1e9, 1) if b else None})
     top = kernels[0]
@@ -249,9 +261,9 @@ def run_b200(args, rank, world, local_rank):
     # whole-frame figure against SURVEY 8d's B_frame (no removeStatic at c2: N-term dropped)
     P = (grid["key_bits"] + 9) // 10
     b_frame = (152 + 16 * P) * M + 16 * grid["coarse_cells"] + 44 * K
-    frame_us = ms_max * 1e3 / (args.steps * F)
-    whole = {"alg_bytes_per_frame": b_frame, "frame_us": round(frame_us, 1), "gbs": round(b_frame / (frame_us * 1e-6) / 1e9, 1),
-             "frac": round(b_frame / (frame_us * 1e-6) / 1e9 / peak, 4)}
+    step_us = ms_max * 1e3 / args.steps
+    whole = {"alg_bytes_per_step": b_frame, "step_us": round(step_us, 1), "gbs": round(b_frame / (step_us * 1e-6) / 1e9, 1),
+             "frac": round(b_frame / (step_us * 1e-6) / 1e9 / peak, 4)}
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -259,12 +271,13 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": make_config(p, n_pts, F, world),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": F * n_pts * 16, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
-                "api": "mot_cluster (host pinned buffers in, CSR out)"},
+                "api": "mot_cluster_batch (host pinned buffers in, CSR out)"},
+        "single_frame_latency_us": round(single_frame_us, 1),
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
         "frame_roofline": whole,
-        "kernels": kernels[:12],
+        "kernels": kernels[:14],
         "wall_ms_per_step": round(wall_max / args.steps, 4),
         "result": {"kept_points": M, "clusters": K, "indices": total, **grid},
     }

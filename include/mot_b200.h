@@ -152,7 +152,8 @@ int mot_host_unregister(void* ptr);
 /* ---- frame batches (BASELINE config 3: multi-LiDAR / multi-sequence streams).  n_frames clouds are
  * concatenated in xyz16; frame f owns points [frame_offsets[f], frame_offsets[f+1]).  Frames never share
  * clusters.  cluster c belongs to frame f iff frame_cluster_offsets[f] <= c < frame_cluster_offsets[f+1];
- * point_indices are positions inside the owning frame's cloud.  No removeStatic (apply it per frame). */
+ * point_indices are positions inside the owning frame's cloud.  No removeStatic (apply it per frame).
+ * mot_cluster_stats / mot_result_fetch give the per-cluster table of the whole batch (same cluster order). */
 int mot_cluster_batch(mot_handle* h, const float* xyz16, const int64_t* frame_offsets, int n_frames,
                       int32_t* frame_cluster_offsets /* n_frames+1 */, int32_t* cluster_offsets,
                       size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters);

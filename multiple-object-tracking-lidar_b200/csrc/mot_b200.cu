@@ -245,7 +245,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
     if (h->uf_mode == 1) {
         int rgrid = (M + 15) / 16;
-        if (rgrid > h->num_sms * 8) rgrid = h->num_sms * 8;
+        if (rgrid > h->num_sms * 32) rgrid = h->num_sms * 32;
         LAUNCH(KID_COARSE_REC, k_coarse_records<KT><<<rgrid, 256, 0, st>>>(skeys, h->d_fc_start, h->d_cc_first, h->d_counts,
                                                                            reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift, g,
                                                                            h->d_crec, h->d_nbr));
@@ -355,6 +355,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_K = K;
     h->res_total = total;
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
+    if (h->h_pinned[8 + CNT_FLAGS] & 2) return fail(h, MOT_ERR_CUDA, "radix sort look-back exceeded its spin limit");
     h->res_fine = h->h_pinned[8 + CNT_FINE];
     h->res_coarse = h->h_pinned[8 + CNT_COARSE];
     h->res_key_bits = total_bits;
@@ -381,20 +382,18 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     LAUNCH(KID_POINT_RANK, k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_vals[h->sorted_buf], h->d_root, h->d_crank, h->d_cmin, M, K, pk[0],
                                                                         h->d_labels));
     h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, h->prof, KID_PART_HIST);
-    if (n_frames > 1 && total > 0) {
-        LAUNCH(KID_LOCALIZE, k_localize_indices<<<(total + 255) / 256, 256, 0, st>>>(h->d_vals[h->res_idx_buf], total, h->d_frame_offsets, n_frames));
-    }
     CK(cudaEventRecord(h->ev[4], st));
 
-    // ---- K7 / K8 ----
-    if (K > 0 && n_frames == 1) {
+    // ---- K7 / K8 (on global point indices; batch indices are made frame-local afterwards) ----
+    if (K > 0) {
         int slabs = 1;
-        if (with_centroids && K < 2000) {
+        const bool cent = with_centroids && n_frames == 1;
+        if (cent && K < 2000) {
             slabs = (h->num_sms * 16 + K - 1) / K;
             if (slabs > 64) slabs = 64;
             if (slabs < 1) slabs = 1;
         }
-        rc = ensure_tables(h, (size_t)K, with_centroids ? (size_t)K * slabs : 0);
+        rc = ensure_tables(h, (size_t)K, cent ? (size_t)K * slabs : 0);
         if (rc != MOT_OK) return rc;
         int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
         LAUNCH(KID_STATS_INIT, k_stats_init<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, K));
@@ -402,13 +401,16 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         LAUNCH(KID_STATS, k_stats_accumulate<<<(total + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf],
                                                                                                          K, total, h->d_statacc));
         LAUNCH(KID_STATS_FIN, k_stats_finalize<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, h->d_cl_offsets, K, h->d_stats));
-        if (with_centroids) {
+        if (cent) {
             LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
                                                                                        h->d_cands));
             LAUNCH(KID_CIRCUMCENTRE, k_circumcentre<<<sgrid, CC_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
                                                                                  h->d_cands, (float)stamp, h->d_centroids));
             h->res_centroids = true;
         }
+    }
+    if (n_frames > 1 && total > 0) {
+        LAUNCH(KID_LOCALIZE, k_localize_indices<<<(total + 255) / 256, 256, 0, st>>>(h->d_vals[h->res_idx_buf], total, h->d_frame_offsets, n_frames));
     }
     CK(cudaEventRecord(h->ev[5], st));
     CK(cudaGetLastError());
@@ -467,7 +469,6 @@ int fetch_result(mot_handle* h, float* kept, size_t kept_cap, int32_t* offs, siz
     }
     if (stats && h->res_K) {
         if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "stats buffer too small");
-        if (h->res_frames != 1) return fail(h, MOT_ERR_STATE, "per-cluster tables are not produced in batch mode");
         CK(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->res_K * sizeof(ClusterStat), cudaMemcpyDefault, st));
     }
     if (cent && h->res_K) {
@@ -558,11 +559,16 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->hash_capacity = (size_t)1 << hb;
         CK(cudaMalloc(&h->d_hkeys, h->hash_capacity * 8));
         CK(dalloc(&h->d_hvals, h->hash_capacity));
+        CK(dalloc(&h->d_counts, (size_t)CNT_N));
         CK(dalloc(&h->rws.hist, rs_workspace_counters()));
         CK(dalloc(&h->rws.prefix, rs_workspace_counters()));
         CK(dalloc(&h->rws.tot, (size_t)1 << RS_MAX_BITS));
+        CK(dalloc(&h->rws.ghist, (size_t)OS_MAX_PASSES * ((size_t)1 << RS_MAX_BITS) + OS_MAX_PASSES));
+        h->rws.status_words = (size_t)OS_MAX_PASSES * ((n + OS_TILE - 1) / OS_TILE + 1) * ((size_t)1 << RS_MAX_BITS);
+        CK(dalloc(&h->rws.status, h->rws.status_words));
+        h->rws.err_flag = h->d_counts + CNT_FLAGS;
+        if (const char* e = getenv("MOT_SORT_MODE")) h->rws.mode = atoi(e);
         CK(dalloc(&h->d_blk, (size_t)4 * 1024));
-        CK(dalloc(&h->d_counts, (size_t)CNT_N));
         CK(dalloc(&h->d_bbox, (size_t)8));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));
         h->frame_capacity = 4096;
@@ -602,7 +608,7 @@ int mot_destroy(mot_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* ptrs[] = {h->d_in, h->d_pts, h->d_spts, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_ckeys[0], h->d_ckeys[1],
                     h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
-                    h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->d_blk,
+                    h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->rws.ghist, h->rws.status, h->d_blk,
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel};
     for (void* p : ptrs)

@@ -222,16 +222,271 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
     }
 }
 
+// ---- onesweep: one kernel per pass, decoupled look-back instead of the per-block histogram matrix ----------------
+//
+// k_os_hist reads the keys once and accumulates the GLOBAL digit histogram of every pass.  A pass is then a single
+// launch of k_os_pass: a CTA takes the next tile (ticket from an atomic counter, so every predecessor tile is already
+// running or done), ranks its 4096 pairs (match.any + per-warp counters, stable), publishes the tile's digit counts,
+// obtains its exclusive prefix per digit by walking back over the predecessors' status words (aggregate / inclusive
+// prefix packed with a 2-bit flag in one 32-bit word, so no fences are needed), and scatters through shared memory.
+// Keys move HBM -> SM -> HBM once per pass; nothing else is re-read.
+constexpr int OS_THREADS = 256;
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_ITEMS = 8;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;  // 2048 pairs per tile
+constexpr int OS_MAX_PASSES = 7;
+constexpr unsigned OS_FLAG_AGG = 1u << 30, OS_FLAG_INCL = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+constexpr int OS_SPIN_LIMIT = 1 << 24;  // a stuck look-back raises an error flag instead of hanging the GPU
+
+struct OsPlan {
+    int passes;
+    int shift[OS_MAX_PASSES];
+    int bits[OS_MAX_PASSES];
+};
+inline OsPlan os_plan(int key_bits) {
+    OsPlan p;
+    if (key_bits < 1) key_bits = 1;
+    p.passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const int base = key_bits / p.passes, rem = key_bits % p.passes;
+    int sh = 0;
+    for (int i = 0; i < p.passes; ++i) {
+        p.bits[i] = base + (i < rem ? 1 : 0);
+        p.shift[i] = sh;
+        sh += p.bits[i];
+    }
+    return p;
+}
+
+// ghist[pass][1 << RS_MAX_BITS]; one launch covers up to 4 passes (pass p0 .. p0+NP-1), shifts/widths in registers
+struct OsHistArgs { int shift[4]; int bits[4]; };
+template <typename KT, int NP>
+__global__ void __launch_bounds__(RS_THREADS) k_os_hist(const KT* __restrict__ keys, int n, int chunk, OsHistArgs a, unsigned* __restrict__ ghist) {
+    extern __shared__ unsigned sh_hist[];  // [NP][1 << RS_MAX_BITS]
+    constexpr int RMAX = 1 << RS_MAX_BITS;
+    for (int d = threadIdx.x; d < NP * RMAX; d += RS_THREADS) sh_hist[d] = 0;
+    __syncthreads();
+    const int begin = blockIdx.x * chunk;
+    const int end = min(n, begin + chunk);
+    const int lane = lane_id();
+    for (int base = begin; base < end; base += RS_TILE) {
+        KT k[RS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            k[j] = i < end ? keys[i] : (KT)0;
+        }
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            const bool valid = i < end;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const unsigned d = valid ? (unsigned)((k[j] >> a.shift[p]) & (KT)((1u << a.bits[p]) - 1u)) : 0xffffffffu;
+                const unsigned peers = __match_any_sync(kFull, d);
+                if (valid && lane == __ffs(peers) - 1) atomicAdd(&sh_hist[p * RMAX + d], (unsigned)__popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < NP * RMAX; d += RS_THREADS) {
+        const unsigned v = sh_hist[d];
+        if (v) atomicAdd(&ghist[d], v);
+    }
+}
+
+template <typename KT>
+inline void os_launch_hist(cudaStream_t st, const KT* keys, int n, const OsPlan& plan, unsigned* ghist, Prof& prof, int kid) {
+    constexpr int RMAX = 1 << RS_MAX_BITS;
+    const Chunking hk = make_chunking(n, RS_TILE, RS_MAX_GRID);
+    for (int p0 = 0; p0 < plan.passes; p0 += 4) {
+        const int np = plan.passes - p0 < 4 ? plan.passes - p0 : 4;
+        OsHistArgs a{};
+        for (int p = 0; p < np; ++p) { a.shift[p] = plan.shift[p0 + p]; a.bits[p] = plan.bits[p0 + p]; }
+        const size_t smem = (size_t)np * RMAX * sizeof(unsigned);
+        unsigned* gh = ghist + (size_t)p0 * RMAX;
+        prof.begin(kid);
+        if (np == 1) k_os_hist<KT, 1><<<hk.grid, RS_THREADS, smem, st>>>(keys, n, hk.chunk, a, gh);
+        else if (np == 2) k_os_hist<KT, 2><<<hk.grid, RS_THREADS, smem, st>>>(keys, n, hk.chunk, a, gh);
+        else if (np == 3) k_os_hist<KT, 3><<<hk.grid, RS_THREADS, smem, st>>>(keys, n, hk.chunk, a, gh);
+        else k_os_hist<KT, 4><<<hk.grid, RS_THREADS, smem, st>>>(keys, n, hk.chunk, a, gh);
+        prof.end();
+    }
+}
+
+constexpr size_t os_pass_smem_bytes(int bits, size_t key_bytes) {
+    return (size_t)(OS_WARPS + 2) * ((size_t)1 << bits) * 4 + 40 * 4 + (size_t)OS_TILE * 4 + (size_t)OS_TILE * key_bytes;
+}
+
+template <typename KT, bool IOTA>
+__global__ void __launch_bounds__(OS_THREADS) k_os_pass(const KT* __restrict__ kin, const uint32_t* __restrict__ vin, KT* __restrict__ kout,
+                                                         uint32_t* __restrict__ vout, int n, int shift, int bits,
+                                                         const unsigned* __restrict__ ghist, unsigned* status, unsigned* tile_counter,
+                                                         int* err_flag) {
+    extern __shared__ __align__(16) unsigned char os_smem[];
+    const int R = 1 << bits;
+    const unsigned mask = R - 1;
+    unsigned* cnt = reinterpret_cast<unsigned*>(os_smem);  // [OS_WARPS][R]
+    unsigned* tile_off = cnt + OS_WARPS * R;               // [R]
+    unsigned* gbase = tile_off + R;                        // [R]
+    int* scan_tmp = reinterpret_cast<int*>(gbase + R);     // [40]; [36] holds the tile ticket
+    uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 40);
+    KT* st_keys = reinterpret_cast<KT*>(st_vals + OS_TILE);
+
+    const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const int per = (R + OS_THREADS - 1) / OS_THREADS;  // digits owned by a thread (<= 4)
+    const int d0 = tid * per;
+
+    if (tid == 0) scan_tmp[36] = (int)atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < OS_WARPS * R; i += OS_THREADS) cnt[i] = 0;
+    // first key of every digit in the output = exclusive scan of the global histogram
+    {
+        int local = 0;
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) local += (int)ghist[d];
+        }
+        int total;
+        int run = block_exclusive_scan(local, scan_tmp, &total);
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) {
+                gbase[d] = (unsigned)run;
+                run += (int)ghist[d];
+            }
+        }
+    }
+    __syncthreads();
+    const int tile = scan_tmp[36];
+    const int tile_begin = tile * OS_TILE;
+    if (tile_begin >= n) return;
+    const int end = min(n, tile_begin + OS_TILE);
+
+    KT key[OS_ITEMS];
+    uint32_t val[OS_ITEMS];
+    unsigned short rank[OS_ITEMS];
+    const int seg = tile_begin + w * (32 * OS_ITEMS);
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const int idx = seg + i * 32 + lane;
+        const bool valid = idx < end;
+        key[i] = valid ? kin[idx] : ~(KT)0;
+        if (IOTA) val[i] = (uint32_t)idx;
+        else val[i] = valid ? vin[idx] : 0u;
+    }
+    unsigned* wcnt = cnt + w * R;
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const int idx = seg + i * 32 + lane;
+        const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;  // padding sorts last
+        const unsigned peers = __match_any_sync(kFull, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned old = 0;
+        if (lane == leader) {
+            old = wcnt[d];
+            wcnt[d] = old + (unsigned)__popc(peers);
+        }
+        old = __shfl_sync(kFull, old, leader);
+        rank[i] = (unsigned short)(old + (unsigned)__popc(peers & lanemask_lt()));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive prefix over the warps, tile count, publish, look back
+    const int n_pad = tile_begin + OS_TILE - end;  // padding items were counted under digit `mask`
+    unsigned mycount[4] = {0, 0, 0, 0};
+    for (int k = 0; k < per; ++k) {  // publish every digit's tile count first ...
+        const int d = d0 + k;
+        if (d >= R) break;
+        unsigned run = 0;
+#pragma unroll
+        for (int ww = 0; ww < OS_WARPS; ++ww) {
+            const unsigned t = cnt[ww * R + d];
+            cnt[ww * R + d] = run;
+            run += t;
+        }
+        mycount[k] = run;
+        const unsigned real = run - ((unsigned)d == mask ? (unsigned)n_pad : 0u);
+        __stcg(status + (size_t)tile * R + d, (tile == 0 ? OS_FLAG_INCL : OS_FLAG_AGG) | real);
+    }
+    if (tile > 0) {
+        for (int k = 0; k < per; ++k) {  // ... then walk back over the predecessors
+            const int d = d0 + k;
+            if (d >= R) break;
+            const unsigned real = mycount[k] - ((unsigned)d == mask ? (unsigned)n_pad : 0u);
+            unsigned excl = 0;
+            int t = tile - 1, spins = 0;
+            for (;;) {
+                const unsigned sv = __ldcg(status + (size_t)t * R + d);
+                const unsigned f = sv >> 30;
+                if (f == 0) {
+                    if (++spins > OS_SPIN_LIMIT) { atomicOr(err_flag, 2); break; }
+                    continue;
+                }
+                excl += sv & OS_VALUE_MASK;
+                if (f == 2 || t == 0) break;
+                --t;
+            }
+            __stcg(status + (size_t)tile * R + d, OS_FLAG_INCL | (excl + real));
+            gbase[d] += excl;
+        }
+    }
+    // exclusive scan of the tile's digit counts -> position of each digit run inside the staged tile
+    {
+        int local = 0;
+        for (int k = 0; k < per; ++k) local += (int)mycount[k];
+        int total;
+        int run = block_exclusive_scan(local, scan_tmp, &total);
+        for (int k = 0; k < per; ++k) {
+            const int d = d0 + k;
+            if (d < R) {
+                tile_off[d] = (unsigned)run;
+                run += (int)mycount[k];
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const int idx = seg + i * 32 + lane;
+        const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;
+        const unsigned pos = tile_off[d] + wcnt[d] + rank[i];
+        st_keys[pos] = key[i];
+        st_vals[pos] = val[i];
+    }
+    __syncthreads();
+    const int tile_n = end - tile_begin;
+    for (int j = tid; j < tile_n; j += OS_THREADS) {
+        const KT k = st_keys[j];
+        const unsigned d = (unsigned)((k >> shift) & mask);
+        const unsigned gpos = gbase[d] + ((unsigned)j - tile_off[d]);
+        kout[gpos] = k;
+        vout[gpos] = st_vals[j];
+    }
+}
+
 struct RadixWorkspace {
     unsigned* hist = nullptr;    // [R_max][G_max]
     unsigned* prefix = nullptr;  // [R_max][G_max]
     unsigned* tot = nullptr;     // [R_max]
+    // onesweep
+    unsigned* ghist = nullptr;   // [OS_MAX_PASSES][R_max] + OS_MAX_PASSES tile counters (zeroed together)
+    unsigned* status = nullptr;  // [passes][tiles][R]
+    size_t status_words = 0;
+    int* err_flag = nullptr;     // device int (bit 1: look-back spin limit hit)
+    int mode = 0;                // 0 = three kernels per pass (default: faster at 1M-8M pairs on B200), 1 = onesweep
 };
 constexpr size_t rs_workspace_counters() { return (size_t)(1 << RS_MAX_BITS) * RS_MAX_GRID; }
 
 template <typename KT>
 inline cudaError_t rs_configure() {
     cudaError_t e;
+    {
+        const int osm = (int)os_pass_smem_bytes(RS_MAX_BITS, sizeof(KT));
+        e = cudaFuncSetAttribute(k_os_pass<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, osm);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_os_pass<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, osm);
+        if (e != cudaSuccess) return e;
+    }
     const int smem = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT));
     e = cudaFuncSetAttribute(k_rs_scatter<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -245,6 +500,35 @@ template <typename KT>
 inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, int key_bits, bool iota_first,
                             const RadixWorkspace& ws, Prof& prof, int kid_base) {
     if (key_bits < 1) key_bits = 1;
+    if (ws.mode == 1 && n > 0) {
+        constexpr int RMAX = 1 << RS_MAX_BITS;
+        const OsPlan plan = os_plan(key_bits);
+        const int tiles = (n + OS_TILE - 1) / OS_TILE;
+        size_t need = 0;
+        for (int p = 0; p < plan.passes; ++p) need += (size_t)tiles << plan.bits[p];
+        if (plan.passes <= OS_MAX_PASSES && need <= ws.status_words) {
+            unsigned* counters = ws.ghist + (size_t)OS_MAX_PASSES * RMAX;
+            cudaMemsetAsync(ws.ghist, 0, ((size_t)OS_MAX_PASSES * RMAX + OS_MAX_PASSES) * sizeof(unsigned), st);
+            cudaMemsetAsync(ws.status, 0, need * sizeof(unsigned), st);
+            os_launch_hist<KT>(st, k[0], n, plan, ws.ghist, prof, kid_base);
+            int cur = 0;
+            size_t soff = 0;
+            for (int p = 0; p < plan.passes; ++p) {
+                const size_t smem = os_pass_smem_bytes(plan.bits[p], sizeof(KT));
+                prof.begin(kid_base + 2);
+                if (p == 0 && iota_first)
+                    k_os_pass<KT, true><<<tiles, OS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, plan.shift[p], plan.bits[p],
+                                                                         ws.ghist + (size_t)p * RMAX, ws.status + soff, counters + p, ws.err_flag);
+                else
+                    k_os_pass<KT, false><<<tiles, OS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, plan.shift[p], plan.bits[p],
+                                                                          ws.ghist + (size_t)p * RMAX, ws.status + soff, counters + p, ws.err_flag);
+                prof.end();
+                soff += (size_t)tiles << plan.bits[p];
+                cur ^= 1;
+            }
+            return cur;
+        }
+    }
     const int passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
     const int base = key_bits / passes, rem = key_bits % passes;
     const Chunking ck = make_chunking(n, RS_TILE, RS_MAX_GRID);

@@ -66,6 +66,7 @@ def make_frame_c1(n_points=65536, n_boxes=40, frame=0, box_shift=(0.0, 0.0)):
         edge = layout.uniform(0.3, 1.5, size=2)
         height = layout.uniform(0.5, 2.0)
         cnt = int(layout.integers(3, 601))
+        cnt = max(3, int(cnt * min(1.0, n_points / 65536.0)))  # smaller frames keep the same layout, thinner boxes
         parts.append(_sample_box_surface(rng, (cx, cy), edge, height, cnt))
         centres.append((cx, cy))
     n_noise = n_points // 100

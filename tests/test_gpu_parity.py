@@ -162,6 +162,15 @@ def test_batch_matches_single_frames(trk, oracle, synth):
     trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
     fco, off, idx = trk.extract_batch(frames)
     assert fco[0] == 0 and fco[-1] == len(off) - 1
+    st_batch = trk.cluster_stats()
+    assert len(st_batch) == len(off) - 1
+    for f, fr in enumerate(frames):
+        if len(fr):
+            k0, k1 = fco[f], fco[f + 1]
+            ref = oracle.cluster_stats(fr, off[k0:k1 + 1] - off[k0], idx[off[k0]:off[k1]])
+            assert np.array_equal(st_batch["count"][k0:k1], ref[:, 0].astype(np.int32))
+            np.testing.assert_allclose(st_batch["mean"][k0:k1], ref[:, 1:4], rtol=RTOL, atol=1e-6)
+            assert np.array_equal(st_batch["bbox_min"][k0:k1], ref[:, 4:7]) and np.array_equal(st_batch["bbox_max"][k0:k1], ref[:, 7:10])
     for f, fr in enumerate(frames):
         o1, i1 = trk.extract(fr)
         k0, k1 = fco[f], fco[f + 1]
