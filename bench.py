@@ -145,26 +145,53 @@ def run_b200(args, rank, world, local_rank):
     all_np = np.ascontiguousarray(np.concatenate(frames_np))
     frame_offsets = np.arange(F + 1, dtype=np.int64) * n_pts
     d_all = torch.from_numpy(all_np).to(dev)          # the step's frames, resident in HBM
-    trk = mot.Tracker(device=local_rank, max_points=F * n_pts, max_tracks=0)
-    trk.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
-    table_buf = torch.zeros((1 << 16, 10), dtype=torch.float32, device=dev)
+    S = max(1, args.streams)
+    trks = [mot.Tracker(device=local_rank, max_points=F * n_pts, max_tracks=0) for _ in range(S)]
+    for t_ in trks:
+        t_.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    trk = trks[0]
+    table_bufs = [torch.zeros((1 << 16, 10), dtype=torch.float32, device=dev) for _ in range(S)]
+    gather_lock = threading.Lock()
 
-    def step_device(gather):
+    def step_device(gather, s=0):
         """One pass of the hot path over the step's batch of F frames (frame id rides in the voxel key)."""
-        trk.cluster_batch_device(d_all.data_ptr(), frame_offsets)
-        launches = trk.last_launches()
+        tk, table_buf = trks[s], table_bufs[s]
+        tk.cluster_batch_device(d_all.data_ptr(), frame_offsets)
+        launches = tk.last_launches()
         if gather:
-            M, K, total = trk.result_counts()
+            M, K, total = tk.result_counts()
             k = min(K, table_buf.shape[0])
             if k:
-                trk.lib.mot_result_fetch(trk.h, None, 0, None, 0, None, 0, table_buf.data_ptr(), None, k)
-            cnt = torch.tensor([k], dtype=torch.int64, device=dev)
-            shard.gather_tables(cnt, table_buf[:k], device=dev)
+                tk.lib.mot_result_fetch(tk.h, None, 0, None, 0, None, 0, table_buf.data_ptr(), None, k)
+            with gather_lock:  # collectives must be issued in the same order on every rank
+                cnt = torch.tensor([k], dtype=torch.int64, device=dev)
+                shard.gather_tables(cnt, table_buf[:k], device=dev)
         return launches
 
+    def run_steps(fn, n_steps):
+        """n_steps steps spread round-robin over the S handles (one host thread + one CUDA stream each): while one
+        batch waits on a host round trip or a PCIe copy, the other keeps the SMs busy."""
+        if S == 1:
+            return sum(fn(0) for _ in range(n_steps))
+        acc = [0] * S
+
+        def worker(s):
+            for i in range(s, n_steps, S):
+                acc[s] += fn(s)
+
+        th = [threading.Thread(target=worker, args=(s,)) for s in range(S)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        return sum(acc)
+
     gather = world > 1
-    for _ in range(max(args.warmup, 3)):
-        step_device(gather)
+    if gather and S > 1:
+        # with several host threads the NCCL gathers of different streams could interleave differently on different
+        # ranks; keep the multi-GPU run on one stream per rank
+        S = 1
+    run_steps(lambda s: step_device(gather, s), max(args.warmup, 3) * S)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -172,9 +199,7 @@ def run_b200(args, rank, world, local_rank):
     sampler.start()
     t_wall0 = time.perf_counter()
     trk.timer_start()
-    launches = 0
-    for _ in range(args.steps):
-        launches += step_device(gather)
+    launches = run_steps(lambda s: step_device(gather, s), args.steps)
     ms = trk.timer_stop()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -190,26 +215,24 @@ def run_b200(args, rank, world, local_rank):
     # ---- e2e: host buffers through mot_cluster_batch (pinned), copies inside the timed region ----
     import ctypes as C
     h_all = torch.from_numpy(all_np).pin_memory()
-    h_fco = torch.empty(F + 1, dtype=torch.int32).pin_memory()
-    h_off = torch.empty(F * n_pts + 1, dtype=torch.int32).pin_memory()
-    h_idx = torch.empty(F * n_pts, dtype=torch.int32).pin_memory()
-    kk = C.c_int32(0)
+    h_out = [(torch.empty(F + 1, dtype=torch.int32).pin_memory(), torch.empty(F * n_pts + 1, dtype=torch.int32).pin_memory(),
+              torch.empty(F * n_pts, dtype=torch.int32).pin_memory()) for _ in range(S)]
 
-    def step_e2e():
-        rc = trk.lib.mot_cluster_batch(trk.h, h_all.data_ptr(), frame_offsets, F, h_fco.data_ptr(), h_off.data_ptr(), F * n_pts + 1,
-                                       h_idx.data_ptr(), F * n_pts, C.byref(kk))
-        assert rc == 0, trk.lib.mot_last_error(trk.h)
+    def step_e2e(s=0):
+        h_fco, h_off, h_idx = h_out[s]
+        kk = C.c_int32(0)
+        tk = trks[s]
+        rc = tk.lib.mot_cluster_batch(tk.h, h_all.data_ptr(), frame_offsets, F, h_fco.data_ptr(), h_off.data_ptr(), F * n_pts + 1,
+                                      h_idx.data_ptr(), F * n_pts, C.byref(kk))
+        assert rc == 0, tk.lib.mot_last_error(tk.h)
         return 4 * (F + 1) + 4 * (kk.value + 1) + 4 * int(h_off[kk.value])
 
-    for _ in range(3):
-        step_e2e()
+    run_steps(step_e2e, 3 * S)
     if dist:
         dist.barrier()
-    e2e_steps = max(2, min(args.steps, 10))
+    e2e_steps = max(2 * S, min(args.steps, 12))
     trk.timer_start()
-    d2h_bytes = 0
-    for _ in range(e2e_steps):
-        d2h_bytes += step_e2e()
+    d2h_bytes = run_steps(step_e2e, e2e_steps)
     e_ms = trk.timer_stop()
     te = torch.tensor([e_ms], dtype=torch.float64, device=dev)
     if dist:
@@ -233,7 +256,7 @@ def run_b200(args, rank, world, local_rank):
     trk.set_profiling(True)
     prof_steps = 3
     for _ in range(prof_steps):
-        step_device(False)
+        step_device(False, 0)
     prof = trk.profile()
     trk.set_profiling(False)
     F_prof = 1  # kernel figures are per launch over the whole batch
@@ -273,6 +296,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": F * n_pts * 16, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                 "api": "mot_cluster_batch (host pinned buffers in, CSR out)"},
         "single_frame_latency_us": round(single_frame_us, 1),
+        "streams_per_gpu": S,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
@@ -283,7 +307,8 @@ def run_b200(args, rank, world, local_rank):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(frames_np[0], p)
-    trk.close()
+    for t_ in trks:
+        t_.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -358,6 +383,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=8, help="distinct frames per step per GPU")
+    ap.add_argument("--streams", type=int, default=2, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -141,7 +141,8 @@ int mot_profile_kernels(void);
 const char* mot_profile_kernel_name(int kernel_id);
 int mot_profile_read(mot_handle* h, float* ms_total, int32_t* launches, int capacity);
 
-/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this handle is launched on). */
+/* CUDA-event stopwatch on the handle's stream (the stream every kernel of this handle is launched on).
+ * mot_timer_stop first waits for all work of the process on the device, so it also brackets other handles' streams. */
 int mot_timer_start(mot_handle* h);
 int mot_timer_stop(mot_handle* h, float* ms);
 

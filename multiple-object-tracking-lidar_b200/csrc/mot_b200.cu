@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -874,6 +875,7 @@ int mot_timer_start(mot_handle* h) {
 int mot_timer_stop(mot_handle* h, float* ms) {
     if (!h || !ms) return MOT_ERR_INVALID;
     CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());  // the stopwatch covers every handle / stream of this process on the device
     CK(cudaEventRecord(h->timer_ev[1], h->stream));
     CK(cudaEventSynchronize(h->timer_ev[1]));
     CK(cudaEventElapsedTime(ms, h->timer_ev[0], h->timer_ev[1]));
