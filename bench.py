@@ -51,7 +51,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms from the start of the timed region to the end of the GPU work."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,7 +65,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -321,15 +321,15 @@ def wedge(frame, frac):
 
 
 def cpu_baseline(frame, p):
-    """The oracle's restatement of the reference path (KD-tree built twice + BFS, 1 thread) on an azimuth wedge
-    of the same frame (same point density as the full frame; bounded to ~10-30 s of CPU work)."""
+    """The oracle's restatement of the reference path (KD-tree built twice + BFS, 1 thread -- the reference is single
+    threaded, MOT.cpp:117-121) on one frame of the step (bounded: ~10-15 s of CPU work)."""
     oracle = entry.load_oracle()
-    w = wedge(frame, 1.0 / 4)
+    w = np.ascontiguousarray(frame)  # the whole 2^20-point frame: ~10-15 s of single-thread CPU work
     t0 = time.perf_counter()
     off, idx = oracle.cluster_kdtree(w, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], build_twice=True)
     dt = time.perf_counter() - t0
     return {"value": round(len(w) / dt / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"1/4 azimuth wedge of frame 0 ({len(w)} points, {len(off) - 1} clusters), {dt:.1f} s, oracle KD-tree+BFS restatement of PCL"}
+            "sample": f"frame 0 of the step, all {len(w)} points ({len(off) - 1} clusters), {dt:.1f} s, oracle KD-tree+BFS restatement of PCL"}
 
 
 def run_reference(args, rank, world):
@@ -380,10 +380,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=8, help="distinct frames per step per GPU")
-    ap.add_argument("--streams", type=int, default=2, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
+    ap.add_argument("--streams", type=int, default=4, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
