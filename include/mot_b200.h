@@ -82,6 +82,14 @@ int mot_set_cluster_params(mot_handle* h, float cluster_tolerance, int min_clust
  * input order.  out_xyz16 may alias nothing in xyz16.  *m receives the number kept. */
 int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xyz16, size_t out_capacity, size_t* m);
 
+/* SURVEY 8f-1 ("next" row): replaces pcl::VoxelGrid::setLeafSize + filter (MOT.cpp:452-456; the tracker uses the
+ * leaf (L, L, 20 L), L = voxel_leaf_size).  One centroid per occupied voxel, emitted in ascending voxel index
+ * (ijk = floor(p * inv_leaf) - min_b in fp32, index = i + j*dx + k*dx*dy), exactly PCL's arithmetic; the mean is
+ * accumulated in fp64 (PCL: fp32 in an unspecified order), so coordinates agree to ~1 ulp.  xyz16 / out_xyz16 may be
+ * host or device pointers. */
+int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, float leaf_y, float leaf_z, float* out_xyz16,
+                   size_t out_capacity, size_t* m);
+
 /* Replaces pcl::search::KdTree::setInputCloud + pcl::EuclideanClusterExtraction::extract
  * (MOT.cpp:472-488).  Output is the CSR form of std::vector<pcl::PointIndices>: cluster c owns
  * point_indices[cluster_offsets[c] .. cluster_offsets[c+1]), indices ascending inside a cluster (PCL sorts

@@ -1,6 +1,7 @@
 // mot_b200_pcl.hpp -- header-only C++ adapter over the C ABI (mot_b200.h) that keeps the reference tracker's call
 // sites source compatible (reference src/multiple_object_tracking_lidar.cpp, "MOT.cpp"):
 //
+//   MOT.cpp:452   pcl::VoxelGrid<pcl::PointXYZ> vg; ... vg.filter(cloud_1) ->  mot_b200::VoxelGrid vg(gpu); same calls
 //   MOT.cpp:461   cloud_2 = removeStatic(cloud_1);                       ->  gpu.removeStatic(cloud_1)
 //   MOT.cpp:472   tree->setInputCloud(cloud_filtered);                   ->  accepted, ignored (no KD-tree is built)
 //   MOT.cpp:480   pcl::EuclideanClusterExtraction<pcl::PointXYZ> ec;     ->  mot_b200::EuclideanClusterExtraction ec(gpu);
@@ -132,6 +133,33 @@ class Tracker {
     mot_handle* h_ = nullptr;
     std::size_t max_points_ = 0;
     int data_length_ = 10;
+};
+
+// Drop-in for pcl::VoxelGrid<pcl::PointXYZ> as used at MOT.cpp:452-456.
+class VoxelGrid {
+  public:
+    explicit VoxelGrid(Tracker& t) : t_(t) {}
+    void setInputCloud(const pcl::PointCloud<pcl::PointXYZ>::ConstPtr& cloud) { cloud_ = cloud; }
+    void setInputCloud(const pcl::PointCloud<pcl::PointXYZ>::Ptr& cloud) { cloud_ = cloud; }
+    void setLeafSize(float lx, float ly, float lz) { leaf_[0] = lx; leaf_[1] = ly; leaf_[2] = lz; }
+    void filter(pcl::PointCloud<pcl::PointXYZ>& out) {
+        out.points.clear();
+        if (cloud_) out.header = cloud_->header;
+        if (!cloud_ || cloud_->points.empty()) { out.width = 0; return; }
+        out.points.resize(cloud_->points.size());
+        std::size_t m = 0;
+        t_.check(mot_voxel_grid(t_.handle(), reinterpret_cast<const float*>(cloud_->points.data()), cloud_->points.size(), leaf_[0], leaf_[1],
+                                leaf_[2], reinterpret_cast<float*>(out.points.data()), out.points.size(), &m));
+        out.points.resize(m);
+        out.width = (std::uint32_t)m;
+        out.height = 1;
+        out.is_dense = true;
+    }
+
+  private:
+    Tracker& t_;
+    pcl::PointCloud<pcl::PointXYZ>::ConstPtr cloud_;
+    float leaf_[3] = {0.05f, 0.05f, 1.0f};
 };
 
 // Drop-in for pcl::EuclideanClusterExtraction<pcl::PointXYZ> as used at MOT.cpp:480-488.

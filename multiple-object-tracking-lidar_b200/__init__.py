@@ -80,6 +80,7 @@ SYMBOLS = {
     "mot_set_map": (C.c_int, [_H, _i8, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, _f64, C.c_int]),
     "mot_set_cluster_params": (C.c_int, [_H, C.c_float, C.c_int, C.c_int]),
     "mot_remove_static": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
+    "mot_voxel_grid": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_float, C.c_float, C.c_float, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
     "mot_cluster": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
     "mot_cluster_stats": (C.c_int, [_H, C.c_void_p, _SIZE]),
     "mot_get_centroid": (C.c_int, [_H, C.c_double, C.c_void_p, _SIZE]),
@@ -180,6 +181,15 @@ class Tracker:
         out = np.empty_like(cloud)
         m = _SIZE(0)
         self._ck(self.lib.mot_remove_static(self.h, _ptr(cloud), len(cloud), _ptr(out), len(out), C.byref(m)))
+        return out[: m.value]
+
+    def voxel_grid(self, cloud, leaf_xyz):
+        """vg.setLeafSize(lx, ly, lz); vg.filter(out)  (reference MOT.cpp:452-456)."""
+        cloud = _cloud(cloud)
+        out = np.empty_like(cloud)
+        m = _SIZE(0)
+        self._ck(self.lib.mot_voxel_grid(self.h, _ptr(cloud), len(cloud), np.float32(leaf_xyz[0]), np.float32(leaf_xyz[1]), np.float32(leaf_xyz[2]),
+                                         _ptr(out), len(out), C.byref(m)))
         return out[: m.value]
 
     def extract(self, cloud):

@@ -326,6 +326,64 @@ __global__ void __launch_bounds__(256) k_stats_finalize(const StatAcc* __restric
     out[k] = st;
 }
 
+// ---- VoxelGrid (reference call site MOT.cpp:452-456; PCL VoxelGrid::applyFilter restated) -----------------
+// key = ijk0 + ijk1*div0 + ijk2*div0*div1 with ijk = floor(p * inv_leaf) - min_b in fp32, exactly PCL's arithmetic.
+struct VoxelParams {
+    float inv[3];
+    int minb[3];
+    int mul1, mul2;
+};
+__global__ void __launch_bounds__(256) k_voxel_keys(const float4* __restrict__ pts, int n, VoxelParams vp, uint32_t* __restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = ld_stream(pts + i);
+    const int i0 = (int)floorf(__fmul_rn(p.x, vp.inv[0])) - vp.minb[0];
+    const int i1 = (int)floorf(__fmul_rn(p.y, vp.inv[1])) - vp.minb[1];
+    const int i2 = (int)floorf(__fmul_rn(p.z, vp.inv[2])) - vp.minb[2];
+    keys[i] = (uint32_t)(i0 + i1 * vp.mul1 + i2 * vp.mul2);
+}
+// segment heads of a sorted key array: per-block counts, then starts[v] = first sorted position of voxel v
+__global__ void __launch_bounds__(256) k_seg_count(const uint32_t* __restrict__ skeys, int n, int chunk, int* __restrict__ counts) {
+    __shared__ int red[8];
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int c = 0;
+    for (int j = begin + threadIdx.x; j < end; j += 256) c += (j == 0 || skeys[j] != skeys[j - 1]);
+    c = warp_sum(c);
+    if (lane_id() == 0) red[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        counts[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_seg_write(const uint32_t* __restrict__ skeys, int n, int chunk, const int* __restrict__ counts,
+                                                    int* __restrict__ starts, int* __restrict__ n_segments) {
+    __shared__ int scratch[36];
+    int base = block_prefix_of(counts, blockIdx.x, scratch);
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int tb = begin; tb < end; tb += 256) {
+        const int j = tb + threadIdx.x;
+        const int head = j < end && (j == 0 || skeys[j] != skeys[j - 1]);
+        int total;
+        const int excl = block_exclusive_scan(head, scratch, &total);
+        if (head) starts[base + excl] = j;
+        base += total;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        starts[base] = n;
+        *n_segments = base;
+    }
+}
+// centroid of every voxel from the fp64 accumulators of k_stats_accumulate (PCL divides an fp32 sum by the count)
+__global__ void __launch_bounds__(256) k_voxel_finalize(const StatAcc* __restrict__ acc, const int* __restrict__ starts, int V,
+                                                         float4* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double cnt = (double)(starts[v + 1] - starts[v]);
+    out[v] = make_float4((float)(acc[v].sum[0] / cnt), (float)(acc[v].sum[1] / cnt), (float)(acc[v].sum[2] / cnt), 1.0f);
+}
+
 // ---- K8: the reference's getCentroid (MOT.cpp:708-822) ----------------------------------------------------------
 // Step 1 (farthest pair, O(n^2)) is spread over `slabs` CTAs per cluster (rows i = slab, slab+slabs, ...); each
 // writes its best candidate; step 2/3 (farthest point from the XY line, circumcentre) reduce them per cluster.

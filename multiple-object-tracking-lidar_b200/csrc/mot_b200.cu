@@ -42,14 +42,15 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
     "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_comp_accumulate", "k_kept_list",
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
-    "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step"};
+    "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
+    "k_seg_count", "k_seg_write", "k_voxel_finalize"};
 
 struct mot_handle {
     int device = 0;
@@ -703,6 +704,76 @@ int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xy
         if (M) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, M * 16, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    return MOT_OK;
+}
+
+// VoxelGrid downsample (reference MOT.cpp:452-456, PCL VoxelGrid restated): bbox -> fp32 voxel index -> radix sort ->
+// segment heads -> point-parallel segmented mean.  d_src: cloud on the device (n points).  The result (V centroids in
+// ascending voxel index) is left in h->d_pts; *m_out = V.
+static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx, float ly, float lz, int* m_out) {
+    cudaStream_t st = h->stream;
+    *m_out = 0;
+    if (n == 0) return MOT_OK;
+    int grid = (n + 255) / 256;
+    if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+    LAUNCH(KID_BBOX, k_bbox<<<grid, 256, 0, st>>>(d_src, n, h->d_bbox));
+    CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
+    VoxelParams vp{};
+    const float leaf[3] = {lx, ly, lz};
+    long long div[3];
+    for (int d = 0; d < 3; ++d) {
+        vp.inv[d] = 1.0f / leaf[d];                                                        // inverse_leaf_size_
+        const float mn = ordered_to_float_bits(h->h_pinned[d]), mx = ordered_to_float_bits(h->h_pinned[3 + d]);
+        vp.minb[d] = (int)std::floor(mn * vp.inv[d]);                                      // min_b_
+        const int maxb = (int)std::floor(mx * vp.inv[d]);                                  // max_b_
+        div[d] = (long long)maxb - vp.minb[d] + 1;                                         // div_b_
+    }
+    if (div[0] * div[1] * div[2] > 0x7fffffffll) return fail(h, MOT_ERR_INVALID, "leaf size too small for the cloud extent (voxel index overflows, as in PCL)");
+    vp.mul1 = (int)div[0];
+    vp.mul2 = (int)(div[0] * div[1]);
+    uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
+    LAUNCH(KID_VOX_KEYS, k_voxel_keys<<<(n + 255) / 256, 256, 0, st>>>(d_src, n, vp, keys[0]));
+    const int sb = radix_sort_pairs<uint32_t>(st, keys, h->d_vals, n, ceil_log2(div[0] * div[1] * div[2]), true, h->rws, h->prof, KID_VOX_HIST);
+    const Chunking ck = make_chunking(n, 256, CELL_MAX_GRID);
+    LAUNCH(KID_SEG_COUNT, k_seg_count<<<ck.grid, 256, 0, st>>>(keys[sb], n, ck.chunk, h->d_blk));
+    LAUNCH(KID_SEG_WRITE, k_seg_write<<<ck.grid, 256, 0, st>>>(keys[sb], n, ck.chunk, h->d_blk, h->d_cl_offsets, h->d_counts + CNT_K));
+    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int V = h->h_pinned[8 + CNT_K];
+    int rc = ensure_tables(h, (size_t)V, 0);
+    if (rc != MOT_OK) return rc;
+    LAUNCH(KID_STATS_INIT, k_stats_init<<<(V + 255) / 256, 256, 0, st>>>(h->d_statacc, V));
+    const int per_block = 32 * STAT_GROUPS_PER_WARP * (STAT_THREADS / 32);
+    LAUNCH(KID_STATS, k_stats_accumulate<<<(n + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(d_src, h->d_cl_offsets, h->d_vals[sb], V, n, h->d_statacc));
+    LAUNCH(KID_VOX_FIN, k_voxel_finalize<<<(V + 255) / 256, 256, 0, st>>>(h->d_statacc, h->d_cl_offsets, V, h->d_pts));
+    CK(cudaGetLastError());
+    *m_out = V;
+    return MOT_OK;
+}
+
+int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, float leaf_y, float leaf_z, float* out_xyz16, size_t out_capacity,
+                   size_t* m) {
+    int rc = check_frame_args(h, xyz16, n);
+    if (rc != MOT_OK) return rc;
+    if (!m || !(leaf_x > 0) || !(leaf_y > 0) || !(leaf_z > 0)) return fail(h, MOT_ERR_INVALID, "bad voxel grid arguments");
+    CK(cudaSetDevice(h->device));
+    *m = 0;
+    if (n == 0) return MOT_OK;
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyDefault, h->stream));
+    int V = 0;
+    rc = voxel_grid_device(h, h->d_in, (int)n, leaf_x, leaf_y, leaf_z, &V);
+    if (rc != MOT_OK) return rc;
+    *m = (size_t)V;
+    if (out_xyz16) {
+        if (out_capacity < (size_t)V) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
+        if (V) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, (size_t)V * 16, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    fold_profile(h);
     return MOT_OK;
 }
 

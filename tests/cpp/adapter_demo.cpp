@@ -35,7 +35,15 @@ int main(int argc, char** argv) {
     const double q[4] = {0, 0, 0, 1};
     gpu.setMap(reinterpret_cast<const int8_t*>(mb.data()), W, H, res, ox, oy, q, 2);
 
-    // --- MOT.cpp:459-491, with the GPU objects substituted ---
+    // --- MOT.cpp:451-491, with the GPU objects substituted ---
+    if (argc > 11) {  // optional VoxelGrid stage (MOT.cpp:452-456), leaf (L, L, 20 L)
+        const float VoxelLeafSize = (float)atof(argv[11]);
+        pcl::PointCloud<pcl::PointXYZ> input_cloud = cloud_1;
+        mot_b200::VoxelGrid vg(gpu);
+        vg.setInputCloud(input_cloud.makeShared());
+        vg.setLeafSize(1 * VoxelLeafSize, 1 * VoxelLeafSize, 20 * VoxelLeafSize);
+        vg.filter(cloud_1);
+    }
     pcl::PointCloud<pcl::PointXYZ> cloud_2;
     pcl::PointCloud<pcl::PointXYZ>::Ptr cloud_filtered(new pcl::PointCloud<pcl::PointXYZ>);
     cloud_2 = gpu.removeStatic(cloud_1);

@@ -229,3 +229,29 @@ def test_error_paths(mot, trk):
         small.remove_static(np.ones((10, 4), np.float32))
     assert e.value.code == -4
     small.close()
+
+
+@pytest.mark.parametrize("leaf", [(0.1, 0.1, 2.0), (0.05, 0.05, 1.0), (0.5, 0.5, 0.5)])
+def test_voxel_grid(trk, oracle, synth, leaf):
+    # pcl::VoxelGrid with the tracker's (L, L, 20 L) leaf, ahead of removeStatic (MOT.cpp:452-456)
+    cloud, _ = synth.make_frame_c1()
+    out = trk.voxel_grid(cloud, leaf)
+    ref = oracle.voxel_grid(cloud, leaf)
+    assert len(out) == len(ref) and 0 < len(out) < len(cloud)
+    np.testing.assert_allclose(out[:, :3], ref[:, :3], rtol=RTOL, atol=1e-5)
+    assert len(trk.voxel_grid(np.zeros((0, 4), np.float32), leaf)) == 0
+
+
+def test_voxel_grid_then_frame(trk, oracle, synth):
+    # the whole of clusterPointCloud (MOT.cpp:444-505): VoxelGrid -> removeStatic -> extract -> getCentroid
+    occ, res, origin = synth.make_map_c1()
+    cloud, _ = synth.make_frame_c1()
+    L = 0.05
+    down = trk.voxel_grid(cloud, (L, L, 20 * L))
+    trk.set_map(occ, res, origin[:2], static_tolarance=2)
+    trk.set_cluster_params(0.3, 5, 300)
+    out = trk.frame(down, stamp_minus_time_init=1.0)
+    kept_ref, _ = oracle.remove_static(down, occ, res, origin[:2], static_tolerance=2)
+    off_ref, idx_ref = oracle.cluster_kdtree(kept_ref, 0.3, 5, 300)
+    assert np.array_equal(out["kept"], kept_ref)
+    assert np.array_equal(out["offsets"], off_ref) and np.array_equal(out["indices"], idx_ref)
