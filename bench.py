@@ -150,48 +150,63 @@ def run_b200(args, rank, world, local_rank):
     for t_ in trks:
         t_.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
     trk = trks[0]
-    table_bufs = [torch.zeros((1 << 16, 10), dtype=torch.float32, device=dev) for _ in range(S)]
-    gather_lock = threading.Lock()
+    TABLE_ROWS = 1 << 15
+    n_slots = 2 * S
+    slots = [torch.zeros((TABLE_ROWS, 10), dtype=torch.float32, device=dev) for _ in range(n_slots)]
+    slot_rows = [0] * n_slots
+    slot_full = [threading.Event() for _ in range(n_slots)]
+    slot_free = [threading.Event() for _ in range(n_slots)]
 
-    def step_device(gather, s=0):
-        """One pass of the hot path over the step's batch of F frames (frame id rides in the voxel key)."""
-        tk, table_buf = trks[s], table_bufs[s]
+    def step_device(gather, s=0, step_index=0):
+        """One pass of the hot path over the step's batch of F frames (frame id rides in the voxel key).  With several
+        GPUs the step's cluster table is left in a slot for the gather (done by the main thread in step order)."""
+        tk = trks[s]
         tk.cluster_batch_device(d_all.data_ptr(), frame_offsets)
         launches = tk.last_launches()
         if gather:
+            sl = step_index % n_slots
+            slot_free[sl].wait()
+            slot_free[sl].clear()
             M, K, total = tk.result_counts()
-            k = min(K, table_buf.shape[0])
+            k = min(K, TABLE_ROWS)
             if k:
-                tk.lib.mot_result_fetch(tk.h, None, 0, None, 0, None, 0, table_buf.data_ptr(), None, k)
-            with gather_lock:  # collectives must be issued in the same order on every rank
-                cnt = torch.tensor([k], dtype=torch.int64, device=dev)
-                shard.gather_tables(cnt, table_buf[:k], device=dev)
+                tk.lib.mot_result_fetch(tk.h, None, 0, None, 0, None, 0, slots[sl].data_ptr(), None, k)
+            slot_rows[sl] = k
+            slot_full[sl].set()
         return launches
 
-    def run_steps(fn, n_steps):
+    def run_steps(fn, n_steps, gather=False):
         """n_steps steps spread round-robin over the S handles (one host thread + one CUDA stream each): while one
-        batch waits on a host round trip or a PCIe copy, the other keeps the SMs busy."""
-        if S == 1:
-            return sum(fn(0) for _ in range(n_steps))
+        batch waits on a host round trip or a PCIe copy, the others keep the SMs busy.  With gather=True the main
+        thread gathers every step's table to rank 0 in step order (same collective order on every rank)."""
+        for e in slot_free:
+            e.set()
+        for e in slot_full:
+            e.clear()
         acc = [0] * S
 
         def worker(s):
             for i in range(s, n_steps, S):
-                acc[s] += fn(s)
+                acc[s] += fn(s, i)
 
         th = [threading.Thread(target=worker, args=(s,)) for s in range(S)]
         for t_ in th:
             t_.start()
+        if gather:
+            for i in range(n_steps):
+                sl = i % n_slots
+                slot_full[sl].wait()
+                slot_full[sl].clear()
+                k = slot_rows[sl]
+                cnt = torch.tensor([k], dtype=torch.int64, device=dev)
+                shard.gather_tables(cnt, slots[sl][:k], device=dev)
+                slot_free[sl].set()
         for t_ in th:
             t_.join()
         return sum(acc)
 
     gather = world > 1
-    if gather and S > 1:
-        # with several host threads the NCCL gathers of different streams could interleave differently on different
-        # ranks; keep the multi-GPU run on one stream per rank
-        S = 1
-    run_steps(lambda s: step_device(gather, s), max(args.warmup, 3) * S)
+    run_steps(lambda s, i: step_device(gather, s, i), max(args.warmup, 3) * S, gather)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -199,7 +214,7 @@ def run_b200(args, rank, world, local_rank):
     sampler.start()
     t_wall0 = time.perf_counter()
     trk.timer_start()
-    launches = run_steps(lambda s: step_device(gather, s), args.steps)
+    launches = run_steps(lambda s, i: step_device(gather, s, i), args.steps, gather)
     ms = trk.timer_stop()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -218,7 +233,7 @@ def run_b200(args, rank, world, local_rank):
     h_out = [(torch.empty(F + 1, dtype=torch.int32).pin_memory(), torch.empty(F * n_pts + 1, dtype=torch.int32).pin_memory(),
               torch.empty(F * n_pts, dtype=torch.int32).pin_memory()) for _ in range(S)]
 
-    def step_e2e(s=0):
+    def step_e2e(s=0, step_index=0):
         h_fco, h_off, h_idx = h_out[s]
         kk = C.c_int32(0)
         tk = trks[s]
@@ -256,7 +271,7 @@ def run_b200(args, rank, world, local_rank):
     trk.set_profiling(True)
     prof_steps = 3
     for _ in range(prof_steps):
-        step_device(False, 0)
+        step_device(False, 0, 0)
     prof = trk.profile()
     trk.set_profiling(False)
     F_prof = 1  # kernel figures are per launch over the whole batch
