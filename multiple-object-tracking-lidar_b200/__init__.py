@@ -24,7 +24,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libmot_b200.so")
+LIB_PATH = os.environ.get("MOT_B200_LIB", os.path.join(_HERE, "libmot_b200.so"))  # override: A/B runs of two builds
 CSRC = os.path.join(_HERE, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",

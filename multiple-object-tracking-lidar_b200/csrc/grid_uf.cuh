@@ -236,6 +236,12 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 
 __device__ __forceinline__ bool coop_witness(const float4* __restrict__ spts, int a0, int a1, int b0, int b1, float r2) {
     const int lane = lane_id();
+    {   // probe: 32 scattered (p, q) pairs in one step -- between densely sampled neighbours one of them almost always hits
+        const int na = a1 - a0, nb = b1 - b0;
+        const float4 p = __ldg(spts + a0 + (int)(((unsigned)lane * 2654435761u >> 8) % (unsigned)na));
+        const float4 q = __ldg(spts + b0 + (int)(((unsigned)lane * 40503u + 17u) % (unsigned)nb));
+        if (__any_sync(kFull, dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < r2)) return true;
+    }
     for (int ia = a0; ia < a1; ia += 32) {
         const bool pv = ia + lane < a1;
         const float4 p = pv ? spts[ia + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -395,7 +401,6 @@ struct __align__(16) UfcWarpSmem {
     int cstart[16];            // first sorted point of cell c
     int coff[16];              // position of cell c's first point in the tile; coff[14] = coff[15] = total
     int ffirst[16];            // first fine id of cell c
-    int ownb[12];              // tile position of the first point of A's child j; ownb[n_a] = n_own
     unsigned char attach[UFC_NODES];  // for neighbour node x = c*8 + j: an own child adjacent to it (0xff = none)
     uint64_t bar;
 };
@@ -462,7 +467,6 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             sm.coff[lane] = incl - rec.y;  // lanes >= 14 hold ptot
             sm.ffirst[lane] = rec.z;
         }
-        if (lane <= n_a) sm.ownb[lane] = __ldg(fc_start + ffirst0 + lane) - own0;
         for (int x = lane; x < UFC_NODES / 4; x += 32) reinterpret_cast<uint32_t*>(sm.attach)[x] = 0xffffffffu;
         // ---- stage the forward neighbourhood: TMA bulk copies (one per occupied cell), or plain loads ----
         bool staged = false;
@@ -488,7 +492,8 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
 
         // ---- sweep ----
         unsigned long long comp = 0x8040201008040201ull;  // byte a = mask of A's children connected to child a (warp uniform)
-        for (int t0 = 0; t0 < ptot; t0 += 32) {
+        // with a single child nothing inside A needs testing: start at the first chunk that holds a neighbour's point
+        for (int t0 = n_a == 1 ? (n_own & ~31) : 0; t0 < ptot; t0 += 32) {
             const int t = t0 + lane;
             const bool valid = t < ptot;
             int c = 0, fid = -1 - lane;
@@ -501,42 +506,53 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
                 fid = __float_as_int(q.w);                    // k_cells_write stores the fine cell id in .w
             }
             unsigned hit = 0;  // bit a: some point of A's child a is within tol of q
-            for (int a = 0; a < n_a; ++a) {
-                const int i1 = sm.ownb[a + 1];
-                bool pred = false;
-                for (int i = sm.ownb[a]; i < i1; ++i) {
-                    const float4 pi = sm.tile[i];
-                    pred |= dist2_exact(pi.x, pi.y, pi.z, q.x, q.y, q.z) < r2;
-                }
-                hit |= (unsigned)pred << a;
+            // one flat loop over A's points (p_i is a broadcast LDS.128; its .w carries the child it belongs to, so the
+            // child bit is warp-uniform arithmetic) -- long enough trip counts for the unrolled body to be the one that runs
+#pragma unroll 4
+            for (int i = 0; i < n_own; ++i) {
+                const float4 pi = sm.tile[i];
+                const unsigned bit = 1u << (unsigned)(__float_as_int(pi.w) - ffirst0);
+                if (dist2_exact(pi.x, pi.y, pi.z, q.x, q.y, q.z) < r2) hit |= bit;
             }
             if (!valid) hit = 0;
             const int j = fid - sm.ffirst[c];                 // child index of q's fine cell inside its coarse cell
-            if (valid && c == 0) hit &= (1u << j) - 1u;       // inside A each unordered child pair once (a < j)
-            const unsigned peers = __match_any_sync(kFull, fid);
-            unsigned hm = 0;
-            for (int a = 0; a < n_a; ++a) {
-                const unsigned bal = __ballot_sync(kFull, (hit >> a) & 1u);
-                if (bal & peers) hm |= 1u << a;
-            }
-            const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
-            if (!leader) hm = 0;
-            if (leader) {
-                if (c == 0) hm |= 1u << j;                    // an own child: it joins the children it touches
-                else sm.attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
-            }
-            // children that this fine cell links for the first time -> merge their components (at most n_a - 1 merges
-            // per task; the need is re-evaluated after every merge so duplicates in the same chunk cost nothing)
-            for (;;) {
-                const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
-                const unsigned bm = __ballot_sync(kFull, (hm & ~lowc) != 0u);
-                if (!bm) break;
-                const unsigned m = __shfl_sync(kFull, hm, __ffs(bm) - 1);
-                unsigned nc = 0;
-                for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
-                for (unsigned mm = nc; mm; mm &= mm - 1) {
-                    const int sh = 8 * (__ffs(mm) - 1);
-                    comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
+            // Fast path: once all of A's children are known to be one component (always, when A has a single child) a hit
+            // lane just records one child it touches for its fine cell -- lanes of the same cell may race, every answer
+            // is right because every child leads to the same root.
+            const bool general = (unsigned)(comp & 0xffull) != ((1u << n_a) - 1u);
+            if (!general && hit && c > 0) sm.attach[c * 8 + j] = (unsigned char)(__ffs(hit) - 1);
+            if (general) {
+                if (valid && c == 0) hit &= (1u << j) - 1u;   // inside A each unordered child pair once (a < j)
+                const unsigned peers = __match_any_sync(kFull, fid);
+                unsigned hm = 0;
+                for (int a = 0; a < n_a; ++a) {
+                    const unsigned bal = __ballot_sync(kFull, (hit >> a) & 1u);
+                    if (bal & peers) hm |= 1u << a;
+                }
+                const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
+                if (!leader) hm = 0;
+                if (leader) {
+                    if (c == 0) hm |= 1u << j;                // an own child: it joins the children it touches
+                    else {
+                        // a fine cell can straddle two chunks: whatever it touched before is linked to what it touches now
+                        const unsigned prev = sm.attach[c * 8 + j];
+                        if (prev != 0xffu) hm |= 1u << prev;
+                        sm.attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
+                    }
+                }
+                // children that this fine cell links for the first time -> merge their components (at most n_a - 1
+                // merges per task; the need is re-evaluated after every merge)
+                for (;;) {
+                    const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
+                    const unsigned bm = __ballot_sync(kFull, (hm & ~lowc) != 0u);
+                    if (!bm) break;
+                    const unsigned m = __shfl_sync(kFull, hm, __ffs(bm) - 1);
+                    unsigned nc = 0;
+                    for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
+                    for (unsigned mm = nc; mm; mm &= mm - 1) {
+                        const int sh = 8 * (__ffs(mm) - 1);
+                        comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
+                    }
                 }
             }
         }

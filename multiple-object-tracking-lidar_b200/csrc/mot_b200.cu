@@ -256,7 +256,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
         const size_t usm = UFC_WARPS * sizeof(UfcWarpSmem);
         LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                            h->uf_tma, h->d_dense_list, h->dense_cap));
-        int dgrid = cgrid < h->num_sms * 4 ? cgrid : h->num_sms * 4;
+        int dgrid = cgrid < h->num_sms * 8 ? cgrid : h->num_sms * 8;
         LAUNCH(KID_UF_DENSE1, k_uf_dense<1><<<dgrid, UFC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                             h->d_dense_list, h->dense_cap));
         LAUNCH(KID_FLATTEN1, k_uf_flatten<true><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));

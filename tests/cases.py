@@ -70,6 +70,9 @@ def kat_cases():
     eq = np.concatenate([chain(10, 0.1, start=(0, 5.0 * k, 0)) for k in range(6)])
     eq = eq[rng.permutation(len(eq))]
     cases["equal_sizes"] = (eq, 0.3, 1, 1000, 6)
+    # huge extent with a small tolerance: the voxel key needs more than 32 bits (64-bit key path)
+    wide = np.concatenate([blob(rng, c, 60, 0.08) for c in rng.uniform([-1500, -1500, -20], [1500, 1500, 30], size=(40, 3))])
+    cases["wide_extent_u64_keys"] = (wide, 0.05, 2, 1000, None)
     # random sparse / dense mixtures
     cases["uniform_sparse"] = (cloud(rng.uniform(0, 20, (4000, 3))), 0.5, 1, 100000, None)
     cases["uniform_dense"] = (cloud(rng.uniform(0, 4, (6000, 3))), 0.3, 3, 100000, None)

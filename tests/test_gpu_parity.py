@@ -179,6 +179,17 @@ def test_batch_matches_single_frames(trk, oracle, synth):
         assert np.array_equal(idx[off[k0]:off[k1]], i1)
 
 
+def test_u64_key_path_is_taken(trk, oracle):
+    pts, tol, mn, mx, _ = kat_cases()["wide_extent_u64_keys"]
+    check_extract(trk, oracle, pts, tol, mn, mx)
+    assert trk.result_grid()["key_bits"] > 32
+    # and in batch mode (frame id in the top key bits)
+    trk.set_cluster_params(tol, mn, mx)
+    fco, off, idx = trk.extract_batch([pts, pts[::-1].copy(), pts[:500]])
+    o1, i1 = trk.extract(pts[::-1].copy())
+    assert np.array_equal(off[fco[1]:fco[2] + 1] - off[fco[1]], o1) and np.array_equal(idx[off[fco[1]]:off[fco[2]]], i1)
+
+
 def test_many_clusters_large_k_path(trk, oracle):
     # > 8192 clusters forces the 64-bit radix ordering path
     rng = np.random.default_rng(5)
