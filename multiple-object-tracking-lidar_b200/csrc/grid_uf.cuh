@@ -573,7 +573,11 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             }
         }
         ea[4] = -1; eb[4] = -1;
-        if (lane < n_a) {
+        if (use_tma & 2) {  // timing aid (MOT_UF_TMA=3): drop every edge -- results are wrong, the sweep cost is isolated
+#pragma unroll
+            for (int r = 0; r < 4; ++r) ea[r] = -1;
+        }
+        if (lane < n_a && !(use_tma & 2)) {
             const int rootc = __ffs((unsigned)((comp >> (8 * lane)) & 0xffull)) - 1;
             if (rootc != lane) { ea[4] = ffirst0 + lane; eb[4] = ffirst0 + rootc; }
         }
