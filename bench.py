@@ -303,6 +303,15 @@ def run_b200(args, rank, world, local_rank):
     whole = {"alg_bytes_per_step": b_frame, "step_us": round(step_us, 1), "gbs": round(b_frame / (step_us * 1e-6) / 1e9, 1),
              "frac": round(b_frame / (step_us * 1e-6) / 1e9 / peak, 4)}
 
+    # north_star's sub-target: grid build + union-find against (104 + 16 P) M + 16 C bytes
+    k15 = ("k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count", "k_hash_clear", "k_cells_write",
+           "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_uf_flatten<in-place>", "k_uf_flatten<root>",
+           "k_uf_pairs<1>", "k_uf_pairs<2>")
+    t15_us = sum(v[0] for kname, v in prof.items() if kname in k15) / prof_steps * 1e3
+    b15 = (104 + 16 * P) * M + 16 * grid["coarse_cells"]
+    grid_uf = {"alg_bytes_per_step": b15, "kernel_us_per_step": round(t15_us, 1), "gbs": round(b15 / (t15_us * 1e-6) / 1e9, 1),
+               "frac": round(b15 / (t15_us * 1e-6) / 1e9 / peak, 4), "target_frac": 0.8}
+
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -316,6 +325,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "frame_roofline": whole,
+        "grid_build_union_find_roofline": grid_uf,
         "kernels": kernels[:14],
         "wall_ms_per_step": round(wall_max / args.steps, 4),
         "result": {"kept_points": M, "clusters": K, "indices": total, **grid},

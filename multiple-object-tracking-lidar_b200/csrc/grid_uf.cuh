@@ -23,6 +23,9 @@
 
 namespace mot {
 
+// d_counts layout (ints)
+enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_EDGES = 7, CNT_HB = 8, CNT_N = 16 };
+
 struct GridCodec {
     double minx, miny, minz, inv_e;
     int bx, by, bz;          // coarse-coordinate bits per axis
@@ -150,8 +153,23 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restri
     }
 }
 
+// The coarse-cell hash is sized on the device from the head count k_cells_count just produced (4 slots per occupied
+// coarse cell, so probes stay ~1 and the table of a LiDAR frame stays L2 resident) and cleared here; every later
+// kernel reads log2(size) from d_counts[CNT_HB].
+template <typename KT>
+__global__ void __launch_bounds__(256) k_hash_clear(const int* __restrict__ counts, int n_blocks, int hb_max, KT* __restrict__ hkeys,
+                                                     int* __restrict__ d_counts) {
+    __shared__ int scratch[36];
+    const int n_coarse = block_prefix_of(counts + n_blocks, n_blocks, scratch);
+    int hb = 4;
+    while (hb < hb_max && (1ll << hb) < 4ll * n_coarse) ++hb;
+    if (blockIdx.x == 0 && threadIdx.x == 0) d_counts[CNT_HB] = hb;
+    const size_t size = (size_t)1 << hb;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x) hkeys[i] = ~(KT)0;
+}
+
 // d_counts layout (ints): [0] fine cells, [1] coarse cells, [2] kept clusters, [3] kept points, [4] flags
-enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_N = 8 };
+
 
 template <typename KT>
 __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restrict__ skeys, const uint32_t* __restrict__ svals,
@@ -162,6 +180,11 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
                                                                int* __restrict__ crank, KT* __restrict__ hkeys, int* __restrict__ hvals,
                                                                unsigned hmask, int hshift, int* __restrict__ d_counts) {
     __shared__ int scratch[36];
+    {
+        const int hb = d_counts[CNT_HB];  // set by k_hash_clear
+        hmask = (1u << hb) - 1u;
+        hshift = 32 - hb;
+    }
     int fbase = block_prefix_of(counts, blockIdx.x, scratch);
     int cbase = block_prefix_of(counts + gridDim.x, blockIdx.x, scratch);
     const int begin = blockIdx.x * chunk, end = min(m, begin + chunk);
@@ -274,6 +297,11 @@ __global__ void __launch_bounds__(UF_THREADS) k_uf_pairs(const KT* __restrict__ 
                                                           const KT* __restrict__ hkeys, const int* __restrict__ hvals, unsigned hmask,
                                                           int hshift, const int* __restrict__ d_counts, int* parent, GridCodec g, float r2) {
     __shared__ int cand[UF_WARPS][UF_MAX_CAND];
+    {
+        const int hb = d_counts[CNT_HB];
+        hmask = (1u << hb) - 1u;
+        hshift = 32 - hb;
+    }
     const int n_fine = d_counts[CNT_FINE];
     const int lane = lane_id(), w = warp_id();
     const int n_warps = gridDim.x * UF_WARPS;
@@ -361,6 +389,11 @@ __global__ void __launch_bounds__(256) k_coarse_records(const KT* __restrict__ s
                                                          const KT* __restrict__ hkeys, const int* __restrict__ hvals, unsigned hmask, int hshift,
                                                          GridCodec g, int4* __restrict__ crec, int* __restrict__ nbr) {
     const int n_coarse = d_counts[CNT_COARSE];
+    {
+        const int hb = d_counts[CNT_HB];
+        hmask = (1u << hb) - 1u;
+        hshift = 32 - hb;
+    }
     const int sub = threadIdx.x & 15;
     for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; ci < n_coarse; ci += (gridDim.x * blockDim.x) >> 4) {
         const int f0 = cc_first[ci];

@@ -39,14 +39,14 @@ static_assert(sizeof(mot_cluster_stat) == 40, "stat layout");
 
 // kernel ids for the launch counter / per-kernel profile (mot_profile_read)
 enum KernelId {
-    KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_CELLS_WRITE,
+    KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
     KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
-    "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_comp_accumulate", "k_kept_list",
+    "k_hash_clear", "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_comp_accumulate", "k_kept_list",
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
@@ -221,19 +221,17 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     const uint32_t* svals = h->d_vals[sb];
     h->sorted_buf = sb;
 
-    // coarse-cell hash sized for at most min(M, #coarse cells) entries at load factor <= 0.5
+    // coarse-cell hash: capacity for the worst case, actual size chosen on the device (k_hash_clear)
     long long coarse_cap = (long long)g.ncx * g.ncy * g.ncz * n_frames;
     if (coarse_cap > M || coarse_cap <= 0) coarse_cap = M;
-    int hb = ceil_log2(2 * coarse_cap);
-    if (hb < 4) hb = 4;
-    const size_t hsize = (size_t)1 << hb;
-    if (hsize > h->hash_capacity) return fail(h, MOT_ERR_CAPACITY, "hash table capacity exceeded");
-    CK(cudaMemsetAsync(h->d_hkeys, 0xff, hsize * sizeof(KT), st));
-    const unsigned hmask = (unsigned)(hsize - 1);
-    const int hshift = 32 - hb;
-
+    int hb_max = ceil_log2(4 * coarse_cap);
+    if (hb_max < 4) hb_max = 4;
+    while (((size_t)1 << hb_max) > h->hash_capacity) --hb_max;  // capacity holds >= 2 slots per point: load <= 0.5 always
+    const unsigned hmask = 0;  // both are read from d_counts[CNT_HB] inside the kernels
+    const int hshift = 0;
     const Chunking ck = make_chunking(M, CELL_THREADS, CELL_MAX_GRID);
     LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, M, ck.chunk, h->d_blk));
+    LAUNCH(KID_HASH_CLEAR, k_hash_clear<KT><<<h->num_sms * 2, 256, 0, st>>>(h->d_blk, ck.grid, hb_max, reinterpret_cast<KT*>(h->d_hkeys), h->d_counts));
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
