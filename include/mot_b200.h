@@ -49,6 +49,16 @@ typedef struct mot_cluster_stat {
     float bbox_max[3];
 } mot_cluster_stat;
 
+/* one row per track holding exactly what ObstacleTrack::publishObstacles (MOT.cpp:253-295) writes into a
+ * costmap_converter::ObstacleMsg (48 bytes). */
+typedef struct mot_obstacle {
+    int32_t id;        /* obstacle.id (MOT.cpp:266) */
+    float radius;      /* 0.3 (MOT.cpp:267) */
+    float x, y;        /* polygon.points[0] = filtered position (MOT.cpp:288-290); z = 0 */
+    float vx, vy;      /* velocities.twist.linear (MOT.cpp:272-273); remaining twist components are 0 */
+    float vel_cov[6];  /* diagonal of velocities.covariance: .1 .1 1e9 1e9 1e9 .1 (MOT.cpp:279-284) */
+} mot_obstacle;
+
 /* Stage timings of the last frame call, milliseconds of GPU time (CUDA events). */
 typedef struct mot_timings {
     float remove_static_ms;
@@ -81,6 +91,15 @@ int mot_set_cluster_params(mot_handle* h, float cluster_tolerance, int min_clust
 /* Replaces ObstacleTrack::removeStatic (MOT.cpp:664-706; decl MOT.h:182).  Kept points are written in
  * input order.  out_xyz16 may alias nothing in xyz16.  *m receives the number kept. */
 int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xyz16, size_t out_capacity, size_t* m);
+
+/* SURVEY 8f-3 ("next" row): replaces pcl::fromROSMsg (MOT.cpp:448-449) for the x / y / z FLOAT32 fields of a
+ * sensor_msgs/PointCloud2: data holds n_points records of point_step bytes, off_* are the byte offsets of the three
+ * fields (any alignment), is_bigendian as in the message.  Output is the pcl::PointXYZ layout (pad = 1).  With
+ * drop_nonfinite != 0 points with a NaN/Inf coordinate are removed, order preserved (pcl::removeNaNFromPointCloud);
+ * with 0 they are kept, as fromROSMsg does.  data / out_xyz16 may be host or device pointers. */
+int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, uint32_t point_step, uint32_t off_x,
+                           uint32_t off_y, uint32_t off_z, int is_bigendian, int drop_nonfinite, float* out_xyz16,
+                           size_t out_capacity, size_t* m);
 
 /* SURVEY 8f-1 ("next" row): replaces pcl::VoxelGrid::setLeafSize + filter (MOT.cpp:452-456; the tracker uses the
  * leaf (L, L, 20 L), L = voxel_leaf_size).  One centroid per occupied voxel, emitted in ascending voxel index
@@ -182,6 +201,10 @@ int mot_ihgp_constants(mot_handle* h, int axis, double* consts16);
  * (stack_obj, MOT.h:107).  m_state: T x 4 doubles (m_x[2], m_y[2]), in/out -- the cross-frame carry the
  * reference keeps inside each InfiniteHorizonGP object.  pos_vel: T x 8 floats (pos xyzi, vel xyzi). */
 int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_state, float* pos_vel);
+/* Same step, and additionally the packed obstacle table of SURVEY 8f-4 (one mot_obstacle per track; track_ids may be
+ * NULL, then id = row index): the payload publishObstacles (MOT.cpp:253-295) puts on the wire. */
+int mot_ihgp_step_obstacles(mot_handle* h, const float* rings, int n_tracks, const int32_t* track_ids, double* m_state,
+                            float* pos_vel, mot_obstacle* obstacles);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ MOT_OK = 0
 ERRORS = {-1: "MOT_ERR_INVALID", -2: "MOT_ERR_CUDA", -3: "MOT_ERR_CAPACITY", -4: "MOT_ERR_NO_MAP", -5: "MOT_ERR_STATE",
           -6: "MOT_ERR_NONFINITE"}
 
+OBSTACLE_DTYPE = np.dtype([("id", np.int32), ("radius", np.float32), ("x", np.float32), ("y", np.float32), ("vx", np.float32), ("vy", np.float32),
+                           ("vel_cov", np.float32, 6)])
 STAT_DTYPE = np.dtype([("count", np.int32), ("mean", np.float32, 3), ("bbox_min", np.float32, 3), ("bbox_max", np.float32, 3)])
 
 
@@ -80,6 +82,9 @@ SYMBOLS = {
     "mot_set_map": (C.c_int, [_H, _i8, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, _f64, C.c_int]),
     "mot_set_cluster_params": (C.c_int, [_H, C.c_float, C.c_int, C.c_int]),
     "mot_remove_static": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
+    "mot_unpack_pointcloud2": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, _SIZE,
+                                         C.POINTER(_SIZE)]),
+    "mot_ihgp_step_obstacles": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mot_voxel_grid": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_float, C.c_float, C.c_float, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
     "mot_cluster": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
     "mot_cluster_stats": (C.c_int, [_H, C.c_void_p, _SIZE]),
@@ -181,6 +186,15 @@ class Tracker:
         out = np.empty_like(cloud)
         m = _SIZE(0)
         self._ck(self.lib.mot_remove_static(self.h, _ptr(cloud), len(cloud), _ptr(out), len(out), C.byref(m)))
+        return out[: m.value]
+
+    def unpack_pointcloud2(self, data, n_points, point_step, off_xyz, is_bigendian=False, drop_nonfinite=False):
+        """pcl::fromROSMsg(*input, input_cloud) for a sensor_msgs/PointCloud2 payload (reference MOT.cpp:448-449)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.empty((max(n_points, 1), 4), dtype=np.float32)
+        m = _SIZE(0)
+        self._ck(self.lib.mot_unpack_pointcloud2(self.h, _ptr(data), int(n_points), int(point_step), int(off_xyz[0]), int(off_xyz[1]), int(off_xyz[2]),
+                                                 int(is_bigendian), int(drop_nonfinite), _ptr(out), len(out), C.byref(m)))
         return out[: m.value]
 
     def voxel_grid(self, cloud, leaf_xyz):
@@ -339,6 +353,16 @@ class Tracker:
         out = np.zeros((T, 8), dtype=np.float32)
         self._ck(self.lib.mot_ihgp_step(self.h, _ptr(rings), T, _ptr(m_state), _ptr(out)))
         return out
+
+    def ihgp_step_obstacles(self, rings, m_state, track_ids=None):
+        """ihgp_step + the packed ObstacleMsg table (publishObstacles, reference MOT.cpp:253-295)."""
+        rings = np.ascontiguousarray(rings, dtype=np.float32)
+        T = rings.shape[0]
+        out = np.zeros((T, 8), dtype=np.float32)
+        obs = np.zeros(max(T, 1), dtype=OBSTACLE_DTYPE)
+        ids = np.ascontiguousarray(track_ids, dtype=np.int32) if track_ids is not None else None
+        self._ck(self.lib.mot_ihgp_step_obstacles(self.h, _ptr(rings), T, _ptr(ids), _ptr(m_state), _ptr(out), _ptr(obs)))
+        return out, obs[:T]
 
 
 from . import synth  # noqa: E402,F401

@@ -19,11 +19,22 @@ struct IhgpAxis {
     double A[4], AKHA[4], K[2], G[4];
 };
 
+// one row per track with exactly what ObstacleTrack::publishObstacles (MOT.cpp:253-295) writes into a
+// costmap_converter::ObstacleMsg, so a ROS shim is a field-by-field copy.  == mot_obstacle in mot_b200.h
+struct ObstacleRow {
+    int id;             // obstacle.id            (MOT.cpp:266)
+    float radius;       // 0.3                    (MOT.cpp:267)
+    float x, y;         // polygon.points[0].x/y  (MOT.cpp:288-290), z = 0
+    float vx, vy;       // velocities.twist.linear.x/y (MOT.cpp:272-273), the other twist components = 0
+    float vel_cov[6];   // diagonal of velocities.covariance: .1, .1, 1e9, 1e9, 1e9, .1 (MOT.cpp:279-284)
+};
+
 constexpr int IHGP_WARPS = 4;
 
 __global__ void __launch_bounds__(IHGP_WARPS * 32) k_ihgp_step(const float4* __restrict__ rings, int T, int L, float dt_gp, float lpf_tau,
                                                                 IhgpAxis ax, IhgpAxis ay, double* __restrict__ m_state,
-                                                                float4* __restrict__ pos_vel) {
+                                                                float4* __restrict__ pos_vel, const int* __restrict__ ids,
+                                                                ObstacleRow* __restrict__ obstacles) {
     extern __shared__ double ihgp_smem[];
     const int n = L - 1;
     double* wbase = ihgp_smem + (size_t)warp_id() * n * 6;
@@ -77,6 +88,15 @@ __global__ void __launch_bounds__(IHGP_WARPS * 32) k_ihgp_step(const float4* __r
             v4.x = vel; v4.y = vy; v4.z = 0.0f; v4.w = b.w;
             pos_vel[(size_t)t * 2] = pos;
             pos_vel[(size_t)t * 2 + 1] = v4;
+            if (obstacles) {
+                ObstacleRow o;
+                o.id = ids ? ids[t] : t;
+                o.radius = 0.3f;
+                o.x = pos.x; o.y = pos.y;
+                o.vx = vel; o.vy = vy;
+                o.vel_cov[0] = 0.1f; o.vel_cov[1] = 0.1f; o.vel_cov[2] = 1e9f; o.vel_cov[3] = 1e9f; o.vel_cov[4] = 1e9f; o.vel_cov[5] = 0.1f;
+                obstacles[t] = o;
+            }
         }
         __syncwarp();
     }

@@ -36,13 +36,14 @@ using namespace mot;
 
 static_assert(sizeof(mot_cluster_stat) == sizeof(ClusterStat), "stat layout");
 static_assert(sizeof(mot_cluster_stat) == 40, "stat layout");
+static_assert(sizeof(mot_obstacle) == sizeof(ObstacleRow) && sizeof(mot_obstacle) == 48, "obstacle layout");
 
 // kernel ids for the launch counter / per-kernel profile (mot_profile_read)
 enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -50,7 +51,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact"};
 
 struct mot_handle {
     int device = 0;
@@ -111,6 +112,10 @@ struct mot_handle {
     float4* d_rings = nullptr;
     double* d_mstate = nullptr;
     float4* d_posvel = nullptr;
+    int* d_track_ids = nullptr;
+    ObstacleRow* d_obstacles = nullptr;
+    uint8_t* d_raw = nullptr;
+    size_t raw_capacity = 0;
     size_t ring_capacity = 0;
 
     // last result
@@ -589,6 +594,8 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         if (max_tracks > 0) {
             CK(dalloc(&h->d_mstate, max_tracks * 4));
             CK(dalloc(&h->d_posvel, max_tracks * 2));
+            CK(dalloc(&h->d_track_ids, max_tracks));
+            CK(dalloc(&h->d_obstacles, max_tracks));
         }
         return MOT_OK;
     };
@@ -610,7 +617,7 @@ int mot_destroy(mot_handle* h) {
                     h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
                     h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->rws.ghist, h->rws.status, h->d_blk,
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
-                    h->d_rings, h->d_mstate, h->d_posvel};
+                    h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -771,6 +778,51 @@ int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, fl
         if (V) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, (size_t)V * 16, cudaMemcpyDefault, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    fold_profile(h);
+    return MOT_OK;
+}
+
+// PointCloud2 wire format -> pcl::PointXYZ on the device (pcl::fromROSMsg, MOT.cpp:448-449).
+int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                           uint32_t off_z, int is_bigendian, int drop_nonfinite, float* out_xyz16, size_t out_capacity, size_t* m) {
+    int rc = check_frame_args(h, data, n_points);
+    if (rc != MOT_OK) return rc;
+    if (!m || point_step < 12 || off_x + 4 > point_step || off_y + 4 > point_step || off_z + 4 > point_step)
+        return fail(h, MOT_ERR_INVALID, "bad PointCloud2 layout");
+    CK(cudaSetDevice(h->device));
+    *m = 0;
+    if (n_points == 0) return MOT_OK;
+    rc = reset_frame_state(h);
+    if (rc != MOT_OK) return rc;
+    const size_t bytes = n_points * (size_t)point_step;
+    if (bytes > h->raw_capacity) {
+        if (h->d_raw) cudaFree(h->d_raw);
+        h->d_raw = nullptr;
+        h->raw_capacity = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&h->d_raw), bytes + 256));
+        h->raw_capacity = bytes;
+    }
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->d_raw, data, bytes, cudaMemcpyDefault, st));
+    const int n = (int)n_points;
+    const Chunking ck = make_chunking(n, 256, RSK_MAX_GRID);
+    LAUNCH(KID_PC2_UNPACK, k_pc2_unpack<<<ck.grid, 256, 0, st>>>(h->d_raw, n, ck.chunk, point_step, off_x, off_y, off_z, is_bigendian, h->d_in, h->d_blk));
+    const float4* result = h->d_in;
+    size_t M = n_points;
+    if (drop_nonfinite) {
+        LAUNCH(KID_PC2_COMPACT, k_pc2_compact<<<ck.grid, 256, 0, st>>>(h->d_in, n, ck.chunk, h->d_blk, h->d_pts, h->d_counts + CNT_M));
+        CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        M = (size_t)h->h_pinned[8 + CNT_M];
+        result = h->d_pts;
+    }
+    CK(cudaGetLastError());
+    *m = M;
+    if (out_xyz16) {
+        if (out_capacity < M) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
+        if (M) CK(cudaMemcpyAsync(out_xyz16, result, M * 16, cudaMemcpyDefault, st));
+    }
+    CK(cudaStreamSynchronize(st));
     fold_profile(h);
     return MOT_OK;
 }
@@ -1083,7 +1135,21 @@ int mot_ihgp_constants(mot_handle* h, int axis, double* consts16) {
     return MOT_OK;
 }
 
+static int ihgp_step_impl(mot_handle* h, const float* rings, int n_tracks, const int32_t* ids, double* m_state, float* pos_vel,
+                          mot_obstacle* obstacles);
+
 int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_state, float* pos_vel) {
+    return ihgp_step_impl(h, rings, n_tracks, nullptr, m_state, pos_vel, nullptr);
+}
+
+int mot_ihgp_step_obstacles(mot_handle* h, const float* rings, int n_tracks, const int32_t* track_ids, double* m_state, float* pos_vel,
+                            mot_obstacle* obstacles) {
+    if (h && !obstacles) return fail(h, MOT_ERR_INVALID, "null obstacle table");
+    return ihgp_step_impl(h, rings, n_tracks, track_ids, m_state, pos_vel, obstacles);
+}
+
+static int ihgp_step_impl(mot_handle* h, const float* rings, int n_tracks, const int32_t* ids, double* m_state, float* pos_vel,
+                          mot_obstacle* obstacles) {
     if (!h) return MOT_ERR_INVALID;
     if (!h->ihgp_ready) return fail(h, MOT_ERR_STATE, "mot_ihgp_configure has not been called");
     if (n_tracks < 0 || (size_t)n_tracks > h->max_tracks) return fail(h, MOT_ERR_CAPACITY, "more tracks than the handle's max_tracks");
@@ -1102,15 +1168,18 @@ int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_sta
     h->prof.launches = 0;
     CK(cudaMemcpyAsync(h->d_rings, rings, ring_elems * 16, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_mstate, m_state, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (obstacles && ids) CK(cudaMemcpyAsync(h->d_track_ids, ids, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (n_tracks + IHGP_WARPS - 1) / IHGP_WARPS;
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0],
-                                                                      h->ihgp_axis[1], h->d_mstate, h->d_posvel));
+                                                                      h->ihgp_axis[1], h->d_mstate, h->d_posvel, (obstacles && ids) ? h->d_track_ids : nullptr,
+                                                                      obstacles ? h->d_obstacles : nullptr));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (obstacles) CK(cudaMemcpyAsync(obstacles, h->d_obstacles, (size_t)n_tracks * sizeof(ObstacleRow), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     fold_profile(h);
     return MOT_OK;

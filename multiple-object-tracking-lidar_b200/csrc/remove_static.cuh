@@ -216,4 +216,73 @@ __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, in
     if (threadIdx.x == 0 && sbad) atomicOr(&bbox[6], 1);
 }
 
+// ---- sensor_msgs/PointCloud2 wire format -> pcl::PointXYZ (what pcl::fromROSMsg does at MOT.cpp:448-449) ----
+// One thread per point: x, y, z FLOAT32 fields at byte offsets off[0..2] inside a point_step-byte record (any alignment,
+// either endianness).  Pass 1 unpacks to float4 (w = 1) and counts the finite points per block; pass 2 is the same stable
+// compaction as removeStatic when non-finite points are to be dropped.
+__device__ __forceinline__ float pc2_load_f32(const uint8_t* p, bool aligned, bool bigendian) {
+    uint32_t v;
+    if (aligned) v = *reinterpret_cast<const uint32_t*>(p);
+    else v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    if (bigendian) v = __byte_perm(v, 0, 0x0123);
+    return __uint_as_float(v);
+}
+__global__ void __launch_bounds__(256) k_pc2_unpack(const uint8_t* __restrict__ data, int n, int chunk, uint32_t point_step, uint32_t off_x,
+                                                     uint32_t off_y, uint32_t off_z, int bigendian, float4* __restrict__ out,
+                                                     int* __restrict__ block_counts) {
+    __shared__ int red[8];
+    const bool aligned = ((point_step | off_x | off_y | off_z) & 3u) == 0u;
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    int cnt = 0;
+    for (int i = begin + threadIdx.x; i < end; i += 256) {
+        const uint8_t* rec = data + (size_t)i * point_step;
+        float4 p;
+        p.x = pc2_load_f32(rec + off_x, aligned, bigendian != 0);
+        p.y = pc2_load_f32(rec + off_y, aligned, bigendian != 0);
+        p.z = pc2_load_f32(rec + off_z, aligned, bigendian != 0);
+        p.w = 1.0f;
+        out[i] = p;
+        cnt += (fabsf(p.x) < INFINITY) && (fabsf(p.y) < INFINITY) && (fabsf(p.z) < INFINITY);
+    }
+    cnt = warp_sum(cnt);
+    if (lane_id() == 0) red[warp_id()] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_pc2_compact(const float4* __restrict__ in, int n, int chunk, const int* __restrict__ block_counts,
+                                                      float4* __restrict__ out, int* __restrict__ total_out) {
+    __shared__ int red[36];
+    __shared__ int wbase[9];
+    int base = block_prefix_of(block_counts, blockIdx.x, red);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = base + block_counts[blockIdx.x];
+    const int begin = blockIdx.x * chunk, end = min(n, begin + chunk);
+    const int lane = lane_id(), w = warp_id();
+    for (int tb = begin; tb < end; tb += 256) {
+        const int i = tb + threadIdx.x;
+        float4 p = make_float4(0, 0, 0, 0);
+        bool keep = false;
+        if (i < end) {
+            p = in[i];
+            keep = (fabsf(p.x) < INFINITY) && (fabsf(p.y) < INFINITY) && (fabsf(p.z) < INFINITY);
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        __syncthreads();
+        if (lane == 0) wbase[w] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) {
+            const int c = wbase[ww];
+            if (ww < w) off += c;
+            tot += c;
+        }
+        if (keep) out[base + off + __popc(bal & lanemask_lt())] = p;
+        base += tot;
+    }
+}
+
 }  // namespace mot

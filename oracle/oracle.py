@@ -201,3 +201,29 @@ def load_map_server_trinary(pgm_path, yaml_path):
     occ[occp < meta["free_thresh"]] = 0
     occ = occ[::-1].copy()  # image row j -> grid row H-1-j
     return occ, float(meta["resolution"]), [float(v) for v in meta["origin"]]
+
+
+def unpack_pointcloud2(data, n_points, point_step, off_xyz, is_bigendian=False, drop_nonfinite=False):
+    """pcl::fromROSMsg restated for the x/y/z FLOAT32 fields of a sensor_msgs/PointCloud2 (reference MOT.cpp:448-449):
+    a field-mapped copy into pcl::PointXYZ (pad = 1); optionally pcl::removeNaNFromPointCloud on top."""
+    raw = np.frombuffer(np.ascontiguousarray(data, dtype=np.uint8).tobytes(), dtype=np.uint8).reshape(n_points, point_step)
+    out = np.ones((n_points, 4), dtype=np.float32)
+    dt = np.dtype(">f4" if is_bigendian else "<f4")
+    for d, off in enumerate(off_xyz):
+        out[:, d] = np.ascontiguousarray(raw[:, off:off + 4]).view(dt).reshape(n_points).astype(np.float32)
+    if drop_nonfinite:
+        out = out[np.isfinite(out[:, :3]).all(axis=1)]
+    return out
+
+
+def obstacle_table(pos_vel, ids):
+    """publishObstacles (reference MOT.cpp:253-295): id, radius 0.3, polygon point = position, twist.linear = velocity,
+    velocity covariance diagonal (.1, .1, 1e9, 1e9, 1e9, .1).  Returns a T x 12 float64 array (id first)."""
+    T = len(pos_vel)
+    out = np.zeros((T, 12))
+    out[:, 0] = ids
+    out[:, 1] = np.float32(0.3)
+    out[:, 2:4] = pos_vel[:, 0:2]
+    out[:, 4:6] = pos_vel[:, 4:6]
+    out[:, 6:12] = np.array([.1, .1, 1e9, 1e9, 1e9, .1], dtype=np.float32)
+    return out

@@ -266,3 +266,43 @@ def test_voxel_grid_then_frame(trk, oracle, synth):
     off_ref, idx_ref = oracle.cluster_kdtree(kept_ref, 0.3, 5, 300)
     assert np.array_equal(out["kept"], kept_ref)
     assert np.array_equal(out["offsets"], off_ref) and np.array_equal(out["indices"], idx_ref)
+
+
+@pytest.mark.parametrize("layout", ["xyz16", "xyzi_rgb32_unaligned", "bigendian"])
+def test_pointcloud2_ingest(trk, oracle, layout):
+    # sensor_msgs/PointCloud2 -> pcl::PointXYZ (pcl::fromROSMsg, MOT.cpp:448-449)
+    rng = np.random.default_rng(9)
+    n = 50000
+    xyz = rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+    xyz[rng.integers(0, n, 300), rng.integers(0, 3, 300)] = np.nan
+    xyz[rng.integers(0, n, 50), 0] = np.inf
+    if layout == "xyz16":
+        step, offs, be = 16, (0, 4, 8), False
+    elif layout == "xyzi_rgb32_unaligned":
+        step, offs, be = 35, (1, 9, 22), False
+    else:
+        step, offs, be = 20, (0, 4, 8), True
+    raw = rng.integers(0, 256, (n, step), dtype=np.uint8)
+    for d, off in enumerate(offs):
+        raw[:, off:off + 4] = xyz[:, d].astype(">f4" if be else "<f4").view(np.uint8).reshape(n, 4)
+    for drop in (False, True):
+        out = trk.unpack_pointcloud2(raw, n, step, offs, is_bigendian=be, drop_nonfinite=drop)
+        ref = oracle.unpack_pointcloud2(raw, n, step, offs, is_bigendian=be, drop_nonfinite=drop)
+        assert out.shape == ref.shape and np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert len(ref) < n
+
+
+def test_obstacle_table(trk, oracle, synth):
+    # the payload of publishObstacles (MOT.cpp:253-295), packed per track by the IHGP kernel
+    T, L = 200, 10
+    hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
+    trk.ihgp_configure(0.1, 0.03, hyp, hyp, L)
+    rings = synth.make_rings_c5(T, L)
+    ids = np.arange(1000, 1000 + T, dtype=np.int32)[::-1].copy()
+    m1, m2 = np.zeros((T, 4)), np.zeros((T, 4))
+    pv, obs = trk.ihgp_step_obstacles(rings, m1, ids)
+    pv2 = trk.ihgp_step(rings, m2)
+    assert np.array_equal(pv, pv2) and np.array_equal(m1, m2)
+    ref = oracle.obstacle_table(pv, ids)
+    got = np.c_[obs["id"], obs["radius"], obs["x"], obs["y"], obs["vx"], obs["vy"], obs["vel_cov"]]
+    assert np.array_equal(got, ref)
