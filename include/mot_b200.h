@@ -206,6 +206,23 @@ int mot_ihgp_step(mot_handle* h, const float* rings, int n_tracks, double* m_sta
 int mot_ihgp_step_obstacles(mot_handle* h, const float* rings, int n_tracks, const int32_t* track_ids, double* m_state,
                             float* pos_vel, mot_obstacle* obstacles);
 
+/* ---- SURVEY 8f-2 ("next" row): data association + track lifecycle on the device.  Replaces the non-first-frame body of
+ * ObstacleTrack::cloudCallback (MOT.cpp:176-233): first-match association in registration order (non exclusive;
+ * tracks registered earlier in the same frame are matchable), fill_with_linear_interpolation (:593-619),
+ * updateObstacleQueue (:586-591), registerNewObstacle (:507-543), callIHGP over this_objIDs (:621-662, a track matched
+ * twice is filtered twice) and unregisterOldObstacle (:545-584, every 5*frequency callbacks, tracks unseen for > 5 s).
+ * The track table (ids, rings of data_length centroids, IHGP state) lives on the device between calls.
+ * centroids_xyzi: n_centroids x 4 floats (x, y, z, intensity = stamp - time_init) in cluster order -- the output of
+ * mot_get_centroid.  now = stamp - time_init.  The first call after mot_tracks_reset (or mot_create) is the reference's
+ * first frame: every centroid registers a track and *produced = 0 (nothing is filtered or published, MOT.cpp:126-161).
+ * Outputs per centroid: this_obj_ids, pos_vel (8 floats, as mot_ihgp_step) and optionally the obstacle table. */
+int mot_tracks_reset(mot_handle* h);
+int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids, double now, float id_threshold,
+                    float frequency, int32_t* this_obj_ids, float* pos_vel, mot_obstacle* obstacles, int32_t* n_tracks,
+                    int32_t* produced);
+/* Copies the track table out (ids, rings n x data_length x 4 floats, m_state n x 4 doubles); any pointer may be NULL. */
+int mot_tracks_get(mot_handle* h, int32_t* ids, float* rings, double* m_state, size_t capacity, int32_t* n_tracks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,30 @@ class Tracker {
         return pos_vel_s;
     }
 
+    // the association / lifecycle / callIHGP part of cloudCallback (MOT.cpp:176-233) with the track table kept
+    // on the device.  Returns false on the reference's "first frame" / "No obstacles around" paths (nothing to publish).
+    bool tracksStep(const std::vector<pcl::PointXYZI>& clusterCentroids, double stamp_minus_time_init, float id_threshold, float frequency,
+                    std::vector<int>& this_objIDs, std::vector<std::vector<pcl::PointXYZI>>& pos_vel_s, std::vector<mot_obstacle>* obstacles = nullptr) {
+        const std::size_t K = clusterCentroids.size();
+        std::vector<float> cen(K * 4), pv(K * 8);
+        for (std::size_t k = 0; k < K; ++k) {
+            cen[4 * k] = clusterCentroids[k].x; cen[4 * k + 1] = clusterCentroids[k].y; cen[4 * k + 2] = clusterCentroids[k].z;
+            cen[4 * k + 3] = clusterCentroids[k].intensity;
+        }
+        this_objIDs.assign(K, -1);
+        if (obstacles) obstacles->resize(K);
+        int32_t n_tracks = 0, produced = 0;
+        check(mot_tracks_step(h_, cen.data(), (int)K, stamp_minus_time_init, id_threshold, frequency, this_objIDs.data(), pv.data(),
+                              obstacles ? obstacles->data() : nullptr, &n_tracks, &produced));
+        pos_vel_s.assign(produced ? K : 0, std::vector<pcl::PointXYZI>(2));
+        for (std::size_t k = 0; produced && k < K; ++k)
+            for (int s = 0; s < 2; ++s) {
+                pcl::PointXYZI& o = pos_vel_s[k][s];
+                o.x = pv[k * 8 + 4 * s]; o.y = pv[k * 8 + 4 * s + 1]; o.z = pv[k * 8 + 4 * s + 2]; o.intensity = pv[k * 8 + 4 * s + 3];
+            }
+        return produced != 0;
+    }
+
     void check(int rc) {
         if (rc != MOT_OK) throw std::runtime_error(std::string("mot_b200: ") + mot_last_error(h_) + " (code " + std::to_string(rc) + ")");
     }

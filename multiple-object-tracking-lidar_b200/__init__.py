@@ -84,6 +84,10 @@ SYMBOLS = {
     "mot_remove_static": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
     "mot_unpack_pointcloud2": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, _SIZE,
                                          C.POINTER(_SIZE)]),
+    "mot_tracks_reset": (C.c_int, [_H]),
+    "mot_tracks_step": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32)]),
+    "mot_tracks_get": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
     "mot_ihgp_step_obstacles": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mot_voxel_grid": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_float, C.c_float, C.c_float, C.c_void_p, _SIZE, C.POINTER(_SIZE)]),
     "mot_cluster": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
@@ -353,6 +357,32 @@ class Tracker:
         out = np.zeros((T, 8), dtype=np.float32)
         self._ck(self.lib.mot_ihgp_step(self.h, _ptr(rings), T, _ptr(m_state), _ptr(out)))
         return out
+
+    def tracks_reset(self):
+        self._ck(self.lib.mot_tracks_reset(self.h))
+
+    def tracks_step(self, centroids, now, id_threshold, frequency):
+        """The association / lifecycle / callIHGP part of cloudCallback (reference MOT.cpp:176-233) on the device.
+        centroids: K x 4 float32 (x, y, z, intensity).  Returns dict(produced, ids, pos_vel, obstacles, n_tracks)."""
+        cen = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, 4)
+        K = len(cen)
+        ids = np.full(max(K, 1), -1, dtype=np.int32)
+        pv = np.zeros((max(K, 1), 8), dtype=np.float32)
+        obs = np.zeros(max(K, 1), dtype=OBSTACLE_DTYPE)
+        n, prod = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.mot_tracks_step(self.h, _ptr(cen), K, float(now), np.float32(id_threshold), np.float32(frequency), _ptr(ids), _ptr(pv),
+                                          _ptr(obs), C.byref(n), C.byref(prod)))
+        return dict(produced=bool(prod.value), ids=ids[:K], pos_vel=pv[:K], obstacles=obs[:K], n_tracks=n.value)
+
+    def tracks_get(self):
+        n = C.c_int32(0)
+        self._ck(self.lib.mot_tracks_get(self.h, None, None, None, 1 << 30, C.byref(n)))
+        T, L = n.value, self.data_length
+        ids = np.zeros(max(T, 1), dtype=np.int32)
+        rings = np.zeros((max(T, 1), L, 4), dtype=np.float32)
+        m = np.zeros((max(T, 1), 4), dtype=np.float64)
+        self._ck(self.lib.mot_tracks_get(self.h, _ptr(ids), _ptr(rings), _ptr(m), max(T, 1), C.byref(n)))
+        return ids[:T], rings[:T], m[:T]
 
     def ihgp_step_obstacles(self, rings, m_state, track_ids=None):
         """ihgp_step + the packed ObstacleMsg table (publishObstacles, reference MOT.cpp:253-295)."""

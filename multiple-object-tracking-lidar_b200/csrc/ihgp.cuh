@@ -34,12 +34,18 @@ constexpr int IHGP_WARPS = 4;
 __global__ void __launch_bounds__(IHGP_WARPS * 32) k_ihgp_step(const float4* __restrict__ rings, int T, int L, float dt_gp, float lpf_tau,
                                                                 IhgpAxis ax, IhgpAxis ay, double* __restrict__ m_state,
                                                                 float4* __restrict__ pos_vel, const int* __restrict__ ids,
-                                                                ObstacleRow* __restrict__ obstacles) {
+                                                                ObstacleRow* __restrict__ obstacles, const int* __restrict__ slot_of_entry,
+                                                                const int* __restrict__ occurrence, int round) {
     extern __shared__ double ihgp_smem[];
     const int n = L - 1;
     double* wbase = ihgp_smem + (size_t)warp_id() * n * 6;
     const int lane = lane_id();
-    for (int t = blockIdx.x * IHGP_WARPS + warp_id(); t < T; t += gridDim.x * IHGP_WARPS) {
+    // Entry e of the call uses the ring / carried state of track slot t (identity unless the on-device association
+    // supplies slot_of_entry; an entry whose track already appeared earlier in the same frame runs in a later round,
+    // exactly as the reference's sequential callIHGP loop would advance that track's state twice).
+    for (int e = blockIdx.x * IHGP_WARPS + warp_id(); e < T; e += gridDim.x * IHGP_WARPS) {
+        if (occurrence && occurrence[e] != round) continue;
+        const int t = slot_of_entry ? slot_of_entry[e] : e;
         const float4* c = rings + (size_t)t * L;
         for (int k = lane; k < n; k += 32) {
             const float4 c0 = c[k], c1 = c[k + 1];
@@ -86,16 +92,16 @@ __global__ void __launch_bounds__(IHGP_WARPS * 32) k_ihgp_step(const float4* __r
             pos.y = __fadd_rn(__fmul_rn(wa, a.y), __fmul_rn(wb, b.y));  // MOT.cpp:828
             pos.z = 0.0f; pos.w = b.w;
             v4.x = vel; v4.y = vy; v4.z = 0.0f; v4.w = b.w;
-            pos_vel[(size_t)t * 2] = pos;
-            pos_vel[(size_t)t * 2 + 1] = v4;
+            pos_vel[(size_t)e * 2] = pos;
+            pos_vel[(size_t)e * 2 + 1] = v4;
             if (obstacles) {
                 ObstacleRow o;
-                o.id = ids ? ids[t] : t;
+                o.id = ids ? ids[e] : e;
                 o.radius = 0.3f;
                 o.x = pos.x; o.y = pos.y;
                 o.vx = vel; o.vy = vy;
                 o.vel_cov[0] = 0.1f; o.vel_cov[1] = 0.1f; o.vel_cov[2] = 1e9f; o.vel_cov[3] = 1e9f; o.vel_cov[4] = 1e9f; o.vel_cov[5] = 0.1f;
-                obstacles[t] = o;
+                obstacles[e] = o;
             }
         }
         __syncwarp();

@@ -31,6 +31,7 @@
 #include "ihgp.cuh"
 #include "radix_sort.cuh"
 #include "remove_static.cuh"
+#include "tracks.cuh"
 
 using namespace mot;
 
@@ -43,7 +44,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -51,7 +52,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge"};
 
 struct mot_handle {
     int device = 0;
@@ -115,6 +116,14 @@ struct mot_handle {
     int* d_track_ids = nullptr;
     ObstacleRow* d_obstacles = nullptr;
     uint8_t* d_raw = nullptr;
+    // on-device track table: ping-pong halves for the purge
+    int* d_trk_ids[2] = {nullptr, nullptr};
+    float4* d_trk_rings[2] = {nullptr, nullptr};
+    double* d_trk_m[2] = {nullptr, nullptr};
+    int *d_trk_meta = nullptr, *d_trk_seen = nullptr, *d_ent_ids = nullptr, *d_ent_slot = nullptr, *d_ent_occ = nullptr;
+    float4* d_centroids_in = nullptr;
+    int trk_cur = 0, trk_L = 0, trk_spin = 0, trk_n = 0;
+    bool trk_first = true;
     size_t raw_capacity = 0;
     size_t ring_capacity = 0;
 
@@ -596,6 +605,17 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
             CK(dalloc(&h->d_posvel, max_tracks * 2));
             CK(dalloc(&h->d_track_ids, max_tracks));
             CK(dalloc(&h->d_obstacles, max_tracks));
+            for (int i = 0; i < 2; ++i) {
+                CK(dalloc(&h->d_trk_ids[i], max_tracks));
+                CK(dalloc(&h->d_trk_m[i], max_tracks * 4));
+            }
+            CK(dalloc(&h->d_trk_meta, (size_t)TM_N));
+            CK(cudaMemset(h->d_trk_meta, 0, TM_N * sizeof(int)));
+            CK(dalloc(&h->d_trk_seen, max_tracks));
+            CK(dalloc(&h->d_ent_ids, max_tracks));
+            CK(dalloc(&h->d_ent_slot, max_tracks));
+            CK(dalloc(&h->d_ent_occ, max_tracks));
+            CK(dalloc(&h->d_centroids_in, max_tracks));
         }
         return MOT_OK;
     };
@@ -617,7 +637,9 @@ int mot_destroy(mot_handle* h) {
                     h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
                     h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->rws.ghist, h->rws.status, h->d_blk,
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
-                    h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw};
+                    h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
+                    h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
+                    h->d_ent_occ, h->d_centroids_in};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1175,13 +1197,114 @@ static int ihgp_step_impl(mot_handle* h, const float* rings, int n_tracks, const
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0],
                                                                       h->ihgp_axis[1], h->d_mstate, h->d_posvel, (obstacles && ids) ? h->d_track_ids : nullptr,
-                                                                      obstacles ? h->d_obstacles : nullptr));
+                                                                      obstacles ? h->d_obstacles : nullptr, nullptr, nullptr, 0));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (obstacles) CK(cudaMemcpyAsync(obstacles, h->d_obstacles, (size_t)n_tracks * sizeof(ObstacleRow), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     fold_profile(h);
+    return MOT_OK;
+}
+
+
+// ---- data association + track lifecycle on the device -----------------------------------------------------
+int mot_tracks_reset(mot_handle* h) {
+    if (!h) return MOT_ERR_INVALID;
+    if (h->max_tracks == 0) return fail(h, MOT_ERR_CAPACITY, "handle was created with max_tracks = 0");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_trk_meta, 0, TM_N * sizeof(int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->trk_cur = 0; h->trk_spin = 0; h->trk_n = 0; h->trk_first = true;
+    return MOT_OK;
+}
+
+int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids, double now, float id_threshold, float frequency,
+                    int32_t* this_obj_ids, float* pos_vel, mot_obstacle* obstacles, int32_t* n_tracks, int32_t* produced) {
+    if (!h) return MOT_ERR_INVALID;
+    if (!h->ihgp_ready) return fail(h, MOT_ERR_STATE, "mot_ihgp_configure has not been called");
+    if (h->max_tracks == 0) return fail(h, MOT_ERR_CAPACITY, "handle was created with max_tracks = 0");
+    if (n_centroids < 0 || (size_t)n_centroids > h->max_tracks) return fail(h, MOT_ERR_CAPACITY, "more centroids than max_tracks");
+    if (produced) *produced = 0;
+    if (n_tracks) *n_tracks = h->trk_n;
+    if (n_centroids == 0) return MOT_OK;  // "No obstacles around": the callback returns before any bookkeeping (MOT.cpp:170-174)
+    if (!centroids_xyzi || !(frequency > 0.0f)) return fail(h, MOT_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int L = h->ihgp_L, K = n_centroids;
+    if (h->trk_L != L) {  // (re)allocate the rings for this data_length; an existing table cannot survive a change of L
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_trk_rings[i]) cudaFree(h->d_trk_rings[i]);
+            h->d_trk_rings[i] = nullptr;
+            CK(dalloc(&h->d_trk_rings[i], h->max_tracks * (size_t)L));
+        }
+        h->trk_L = L;
+        int rc = mot_tracks_reset(h);
+        if (rc != MOT_OK) return rc;
+    }
+    h->prof.launches = 0;
+    const float dt_gp = 1 / frequency;  // MOT.cpp:159
+    const int cur = h->trk_cur;
+    CK(cudaMemcpyAsync(h->d_centroids_in, centroids_xyzi, (size_t)K * 16, cudaMemcpyDefault, st));
+    // first frame: every centroid registers a track, nothing is filtered or published (MOT.cpp:126-161)
+    const float thr = h->trk_first ? -1.0f : id_threshold;
+    LAUNCH(KID_ASSOCIATE, k_associate<<<1, ASSOC_THREADS, 0, st>>>(h->d_centroids_in, K, L, (int)h->max_tracks, thr, dt_gp, h->d_trk_ids[cur],
+                                                                  h->d_trk_rings[cur], h->d_trk_m[cur], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids,
+                                                                  h->d_ent_slot, h->d_ent_occ));
+    CK(cudaMemcpyAsync(h->h_pinned + 32, h->d_trk_meta, TM_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->trk_n = h->h_pinned[32 + TM_NTRACKS];
+    if (n_tracks) *n_tracks = h->trk_n;
+    if (h->h_pinned[32 + TM_OVERFLOW]) return fail(h, MOT_ERR_CAPACITY, "track table full (max_tracks)");
+    if (this_obj_ids) CK(cudaMemcpyAsync(this_obj_ids, h->d_ent_ids, (size_t)K * sizeof(int), cudaMemcpyDefault, st));
+    if (h->trk_first) {
+        h->trk_first = false;
+        CK(cudaStreamSynchronize(st));
+        fold_profile(h);
+        return MOT_OK;
+    }
+    // callIHGP over this_objIDs (MOT.cpp:621-662); a track that was matched twice in this frame is filtered twice, in order
+    const int max_occ = h->h_pinned[32 + TM_MAX_OCC];
+    const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (K + IHGP_WARPS - 1) / IHGP_WARPS;
+    if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+    for (int r = 0; r <= max_occ; ++r)
+        LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_trk_rings[cur], K, L, dt_gp, h->ihgp_tau, h->ihgp_axis[0], h->ihgp_axis[1],
+                                                                          h->d_trk_m[cur], h->d_posvel, h->d_ent_ids, h->d_obstacles, h->d_ent_slot,
+                                                                          h->d_ent_occ, r));
+    if (pos_vel) CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)K * 8 * sizeof(float), cudaMemcpyDefault, st));
+    if (obstacles) CK(cudaMemcpyAsync(obstacles, h->d_obstacles, (size_t)K * sizeof(ObstacleRow), cudaMemcpyDefault, st));
+    // unregisterOldObstacle (MOT.cpp:545-584)
+    h->trk_spin += 1;
+    const double period = 5;
+    if (h->trk_spin > period * frequency) {
+        LAUNCH(KID_TRACKS_PURGE, k_tracks_purge<<<1, ASSOC_THREADS, 0, st>>>(h->d_trk_ids[cur], h->d_trk_rings[cur], h->d_trk_m[cur], h->d_trk_ids[cur ^ 1],
+                                                                            h->d_trk_rings[cur ^ 1], h->d_trk_m[cur ^ 1], L, now, period, h->d_trk_meta));
+        h->trk_cur = cur ^ 1;
+        h->trk_spin = 0;
+        CK(cudaMemcpyAsync(h->h_pinned + 32, h->d_trk_meta, TM_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    h->trk_n = h->h_pinned[32 + TM_NTRACKS];
+    if (n_tracks) *n_tracks = h->trk_n;
+    if (produced) *produced = 1;
+    fold_profile(h);
+    return MOT_OK;
+}
+
+int mot_tracks_get(mot_handle* h, int32_t* ids, float* rings, double* m_state, size_t capacity, int32_t* n_tracks) {
+    if (!h) return MOT_ERR_INVALID;
+    if (n_tracks) *n_tracks = h->trk_n;
+    if ((size_t)h->trk_n > capacity) return fail(h, MOT_ERR_CAPACITY, "track buffers too small");
+    if (h->trk_n == 0) return MOT_OK;
+    CK(cudaSetDevice(h->device));
+    const int cur = h->trk_cur;
+    if (ids) CK(cudaMemcpyAsync(ids, h->d_trk_ids[cur], (size_t)h->trk_n * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (rings) CK(cudaMemcpyAsync(rings, h->d_trk_rings[cur], (size_t)h->trk_n * h->trk_L * 16, cudaMemcpyDefault, h->stream));
+    if (m_state) CK(cudaMemcpyAsync(m_state, h->d_trk_m[cur], (size_t)h->trk_n * 4 * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return MOT_OK;
 }
 

@@ -306,3 +306,61 @@ def test_obstacle_table(trk, oracle, synth):
     ref = oracle.obstacle_table(pv, ids)
     got = np.c_[obs["id"], obs["radius"], obs["x"], obs["y"], obs["vx"], obs["vy"], obs["vel_cov"]]
     assert np.array_equal(got, ref)
+
+
+def _tracker_scenario(seed, n_frames, n_obj, dt=0.1):
+    """Moving objects with drop-outs (gaps > 3 dt trigger the interpolation), births, deaths, two centroids close enough
+    to hit the same track, and a long quiet stretch so that the 5 s purge fires."""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-10, 10, (n_obj, 2))
+    vel = rng.uniform(-1.2, 1.2, (n_obj, 2))
+    born = rng.integers(0, n_frames // 3, n_obj)
+    dies = born + rng.integers(n_frames // 4, n_frames, n_obj)
+    frames = []
+    for f in range(n_frames):
+        t = 100.0 + f * dt
+        cen = []
+        for o in range(n_obj):
+            if not (born[o] <= f < dies[o]):
+                continue
+            if rng.random() < 0.08 or (o % 5 == 0 and 30 <= f % 60 < 36):  # missed detections; periodic 6-frame gaps
+                continue
+            p = pos[o] + vel[o] * (f * dt) + rng.normal(0, 0.01, 2)
+            cen.append([p[0], p[1], 0.0, t])
+            if o % 7 == 0 and f % 11 == 0:
+                cen.append([p[0] + 0.05, p[1] - 0.04, 0.0, t])  # a second centroid inside id_threshold of the same track
+        if 70 <= f < 75:
+            cen = []  # "No obstacles around"
+        frames.append((t, np.array(cen, dtype=np.float32).reshape(-1, 4)))
+    return frames
+
+
+@pytest.mark.parametrize("seed,L", [(1, 10), (2, 40)])
+def test_tracks_association_lifecycle(mot, oracle, seed, L):
+    # SURVEY 8f-2: cloudCallback's association / interpolation / registration / callIHGP / purge, device resident
+    from oracle.tracker_ref import TrackerRef
+    hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
+    freq, thr = 10.0, 0.4
+    t = mot.Tracker(device=0, max_points=1024, max_tracks=512)
+    t.ihgp_configure(0.1, 0.03, hyp, hyp, L)
+    ref = TrackerRef(freq, thr, L, 0.03, hyp, hyp)
+    produced = 0
+    for now, cen in _tracker_scenario(seed, 140, 24):
+        out = t.tracks_step(cen, now, thr, freq)
+        r = ref.step(cen, now)
+        assert out["produced"] == (r is not None)
+        assert out["n_tracks"] == len(ref.obj_ids)
+        if r is not None:
+            produced += 1
+            ids_ref, pv_ref = r
+            assert np.array_equal(out["ids"], ids_ref)
+            np.testing.assert_allclose(out["pos_vel"], pv_ref, rtol=RTOL, atol=1e-6)
+            assert np.array_equal(out["obstacles"]["id"], ids_ref)
+        ids, rings, m = t.tracks_get()
+        assert np.array_equal(ids, np.array(ref.obj_ids, dtype=np.int32))
+        if len(ids):
+            assert np.array_equal(rings.view(np.uint32), np.array(ref.stack, dtype=np.float32).view(np.uint32))  # rings bit-exact
+            np.testing.assert_allclose(m, np.array(ref.m), rtol=RTOL, atol=1e-9)
+    assert produced > 100 and ref.next_obj_num > 24  # births beyond the first frame happened, and the purge ran:
+    assert len(ref.obj_ids) < ref.next_obj_num
+    t.close()

@@ -189,3 +189,35 @@ def test_voxel_grid(oracle):
     np.add.at(ref, inv, xyz.astype(np.float64))
     ref /= np.bincount(inv)[:, None]
     np.testing.assert_allclose(out[:, :3], ref, rtol=1e-5, atol=1e-5)
+
+
+def test_tracker_reference_known_answers():
+    # hand-checkable behaviour of the restated association (MOT.cpp:176-219, 593-619, 545-584)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle.tracker_ref import TrackerRef
+    hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
+    trk = TrackerRef(10.0, 0.4, 5, 0.03, hyp, hyp)
+
+    def cen(rows):
+        return np.array(rows, dtype=np.float32).reshape(-1, 4)
+
+    assert trk.step(cen([]), 0.0) is None and trk.first                      # empty first frame: nothing happens
+    assert trk.step(cen([[0, 0, 0, 1.0], [5, 0, 0, 1.0]]), 1.0) is None        # first frame registers, no output
+    assert trk.obj_ids == [0, 1] and len(trk.stack[0]) == 5
+    ids, pv = trk.step(cen([[5.1, 0, 0, 1.1], [0.1, 0, 0, 1.1], [9, 9, 0, 1.1]]), 1.1)
+    assert ids.tolist() == [1, 0, 2]                                            # first match in registration order; new id for the stranger
+    assert trk.stack[1][-1][0] == np.float32(5.1) and trk.stack[1][0][0] == np.float32(5.0)
+    # two centroids inside id_threshold of track 0 -> both take id 0 (non exclusive), track filtered twice
+    ids, _ = trk.step(cen([[0.15, 0, 0, 1.2], [0.2, 0.05, 0, 1.2]]), 1.2)
+    assert ids.tolist() == [0, 0]
+    # a 0.5 s gap (> 3 dt) on track 1 -> 4 interpolated centroids + the new one: the ring (L = 5) is fully rewritten
+    ids, _ = trk.step(cen([[5.35, 0, 0, 1.6]]), 1.6)
+    assert ids.tolist() == [1]
+    ring = np.array(trk.stack[1])
+    np.testing.assert_allclose(ring[:, 3], [1.2, 1.3, 1.4, 1.5, 1.6], atol=1e-5)
+    np.testing.assert_allclose(np.diff(ring[:4, 0]), (5.35 - 5.1) / 4, atol=1e-5)
+    # nothing is purged before 5 * frequency callbacks; afterwards tracks unseen for > 5 s go
+    for k in range(60):
+        trk.step(cen([[0.2, 0.0, 0, 2.0 + 0.1 * k]]), 2.0 + 0.1 * k)
+    assert trk.obj_ids == [0]
