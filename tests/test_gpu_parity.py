@@ -364,3 +364,34 @@ def test_tracks_association_lifecycle(mot, oracle, seed, L):
     assert produced > 100 and ref.next_obj_num > 24  # births beyond the first frame happened, and the purge ran:
     assert len(ref.obj_ids) < ref.next_obj_num
     t.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_partition_vs_oracle(trk, oracle, seed):
+    # randomised differential test: mixtures of dense blobs, planes, lines and uniform noise at random scales / tolerances;
+    # exercises sparse and dense union-find tasks, 1-3 radix passes, empty / tiny clusters, min/max filters
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(200, 60000))
+    scale = float(10 ** rng.uniform(-1, 2.3))
+    tol = float(scale * 10 ** rng.uniform(-2.5, -0.7))
+    parts = []
+    left = n
+    while left > 0:
+        kind = rng.integers(0, 4)
+        k = int(min(left, rng.integers(1, max(2, n // 3))))
+        c = rng.uniform(-scale, scale, 3)
+        if kind == 0:
+            p = c + rng.normal(0, tol * rng.uniform(0.2, 3), (k, 3))
+        elif kind == 1:
+            p = c + np.c_[rng.uniform(-1, 1, (k, 2)) * scale * rng.uniform(0.01, 0.3), np.zeros(k)]
+        elif kind == 2:
+            p = c + np.outer(np.linspace(0, 1, k), rng.normal(0, 1, 3)) * scale * 0.3
+        else:
+            p = rng.uniform(-scale, scale, (k, 3))
+        parts.append(p)
+        left -= k
+    pts = np.ones((n, 4), np.float32)
+    pts[:, :3] = np.concatenate(parts)[rng.permutation(n)]
+    mn = int(rng.integers(1, 8))
+    mx = int(rng.choice([10, 300, 100000]))
+    check_extract(trk, oracle, pts, tol, mn, mx, brute=n <= 4000)
