@@ -255,6 +255,36 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pts_per_step * e2e_steps / (float(te[0]) * 1e-3) / 1e6
 
+    # ---- the same frames through the per-frame call the reference's callback would make (mot_cluster, one frame per
+    # call, pinned host buffers, H2D + D2H inside the timed region), frames dealt round-robin to the S handles ----
+    small = [mot.Tracker(device=local_rank, max_points=n_pts, max_tracks=0) for _ in range(S)]
+    for t_ in small:
+        t_.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    h_frames = [h_all[f * n_pts:(f + 1) * n_pts] for f in range(F)]
+
+    def frame_e2e(s=0, i=0):
+        _, h_off, h_idx = h_out[s]
+        kk = C.c_int32(0)
+        tk = small[s]
+        rc = tk.lib.mot_cluster(tk.h, h_frames[i % F].data_ptr(), n_pts, h_off.data_ptr(), n_pts + 1, h_idx.data_ptr(), n_pts, C.byref(kk))
+        assert rc == 0, tk.lib.mot_last_error(tk.h)
+        return 0
+
+    run_steps(frame_e2e, 2 * F)
+    if dist:
+        dist.barrier()
+    n_calls = 6 * F
+    trk.timer_start()
+    run_steps(frame_e2e, n_calls)
+    pf_ms = trk.timer_stop()
+    tpf = torch.tensor([pf_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(tpf, op=dist.ReduceOp.MAX)
+    e2e_per_frame = world * n_calls * n_pts / (float(tpf[0]) * 1e-3) / 1e6
+    for t_ in small:
+        t_.close()
+
     # ---- single-frame latency (one 2^20-point frame per call, as the reference's callback sees it) ----
     lat = []
     for f in range(F):
@@ -318,7 +348,8 @@ def run_b200(args, rank, world, local_rank):
         "data": "synthetic",
         "config": make_config(p, n_pts, F, world),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": F * n_pts * 16, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
-                "api": "mot_cluster_batch (host pinned buffers in, CSR out)"},
+                "api": "mot_cluster_batch (host pinned buffers in, CSR out)",
+                "per_frame_api": {"value": round(e2e_per_frame, 2), "unit": UNIT, "api": "mot_cluster, one frame per call"}},
         "single_frame_latency_us": round(single_frame_us, 1),
         "streams_per_gpu": S,
         "gpu_launches": launches,
