@@ -526,7 +526,10 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
         // ---- sweep ----
         unsigned long long comp = 0x8040201008040201ull;  // byte a = mask of A's children connected to child a (warp uniform)
         // with a single child nothing inside A needs testing: start at the first chunk that holds a neighbour's point
-        for (int t0 = n_a == 1 ? (n_own & ~31) : 0; t0 < ptot; t0 += 32) {
+        int t0 = n_a == 1 ? (n_own & ~31) : 0;
+        const unsigned all_children = (1u << n_a) - 1u;
+        // General chunks (32 points, one per lane): as long as A's children are not yet known to be one component.
+        for (; t0 < ptot && (unsigned)(comp & 0xffull) != all_children; t0 += 32) {
             const int t = t0 + lane;
             const bool valid = t < ptot;
             int c = 0, fid = -1 - lane;
@@ -549,44 +552,67 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             }
             if (!valid) hit = 0;
             const int j = fid - sm.ffirst[c];                 // child index of q's fine cell inside its coarse cell
-            // Fast path: once all of A's children are known to be one component (always, when A has a single child) a hit
-            // lane just records one child it touches for its fine cell -- lanes of the same cell may race, every answer
-            // is right because every child leads to the same root.
-            const bool general = (unsigned)(comp & 0xffull) != ((1u << n_a) - 1u);
-            if (!general && hit && c > 0) sm.attach[c * 8 + j] = (unsigned char)(__ffs(hit) - 1);
-            if (general) {
-                if (valid && c == 0) hit &= (1u << j) - 1u;   // inside A each unordered child pair once (a < j)
-                const unsigned peers = __match_any_sync(kFull, fid);
-                unsigned hm = 0;
-                for (int a = 0; a < n_a; ++a) {
-                    const unsigned bal = __ballot_sync(kFull, (hit >> a) & 1u);
-                    if (bal & peers) hm |= 1u << a;
+            if (valid && c == 0) hit &= (1u << j) - 1u;       // inside A each unordered child pair once (a < j)
+            const unsigned peers = __match_any_sync(kFull, fid);
+            unsigned hm = 0;
+            for (int a = 0; a < n_a; ++a) {
+                const unsigned bal = __ballot_sync(kFull, (hit >> a) & 1u);
+                if (bal & peers) hm |= 1u << a;
+            }
+            const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
+            if (!leader) hm = 0;
+            if (leader) {
+                if (c == 0) hm |= 1u << j;                    // an own child: it joins the children it touches
+                else {
+                    // a fine cell can straddle two chunks: whatever it touched before is linked to what it touches now
+                    const unsigned prev = sm.attach[c * 8 + j];
+                    if (prev != 0xffu) hm |= 1u << prev;
+                    sm.attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
                 }
-                const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
-                if (!leader) hm = 0;
-                if (leader) {
-                    if (c == 0) hm |= 1u << j;                // an own child: it joins the children it touches
-                    else {
-                        // a fine cell can straddle two chunks: whatever it touched before is linked to what it touches now
-                        const unsigned prev = sm.attach[c * 8 + j];
-                        if (prev != 0xffu) hm |= 1u << prev;
-                        sm.attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
-                    }
+            }
+            // children that this fine cell links for the first time -> merge their components (at most n_a - 1
+            // merges per task; the need is re-evaluated after every merge)
+            for (;;) {
+                const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
+                const unsigned bm = __ballot_sync(kFull, (hm & ~lowc) != 0u);
+                if (!bm) break;
+                const unsigned m = __shfl_sync(kFull, hm, __ffs(bm) - 1);
+                unsigned nc = 0;
+                for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
+                for (unsigned mm = nc; mm; mm &= mm - 1) {
+                    const int sh = 8 * (__ffs(mm) - 1);
+                    comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
                 }
-                // children that this fine cell links for the first time -> merge their components (at most n_a - 1
-                // merges per task; the need is re-evaluated after every merge)
-                for (;;) {
-                    const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
-                    const unsigned bm = __ballot_sync(kFull, (hm & ~lowc) != 0u);
-                    if (!bm) break;
-                    const unsigned m = __shfl_sync(kFull, hm, __ffs(bm) - 1);
-                    unsigned nc = 0;
-                    for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
-                    for (unsigned mm = nc; mm; mm &= mm - 1) {
-                        const int sh = 8 * (__ffs(mm) - 1);
-                        comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
-                    }
-                }
+            }
+        }
+        // Fast chunks (64 points, two per lane): all of A's children are one component, so a hit lane only has to record
+        // ONE child it touches for its fine cell -- lanes of the same cell may race, every answer leads to the same root.
+        // Own-cell points (c == 0) need nothing any more.  Two points per lane share the broadcast LDS and the loop.
+        for (; t0 < ptot; t0 += 64) {
+            const int ta = t0 + lane, tb = t0 + 32 + lane;
+            const float4 qa = ta < ptot ? sm.tile[ta] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);  // never within tol of anything
+            const float4 qb = tb < ptot ? sm.tile[tb] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+            int ha = -1, hb = -1;  // a child of A within tol of qa / qb
+#pragma unroll 4
+            for (int i = 0; i < n_own; ++i) {
+                const float4 pi = sm.tile[i];
+                const int child = __float_as_int(pi.w) - ffirst0;
+                if (dist2_exact(pi.x, pi.y, pi.z, qa.x, qa.y, qa.z) < r2) ha = child;
+                if (dist2_exact(pi.x, pi.y, pi.z, qb.x, qb.y, qb.z) < r2) hb = child;
+            }
+            if (ha >= 0 && ta >= n_own) {
+                int c = 0;
+#pragma unroll
+                for (int k = 8; k > 0; k >>= 1)
+                    if (c + k < UFC_CELLS && sm.coff[c + k] <= ta) c += k;
+                sm.attach[c * 8 + (__float_as_int(qa.w) - sm.ffirst[c])] = (unsigned char)ha;
+            }
+            if (hb >= 0 && tb >= n_own) {
+                int c = 0;
+#pragma unroll
+                for (int k = 8; k > 0; k >>= 1)
+                    if (c + k < UFC_CELLS && sm.coff[c + k] <= tb) c += k;
+                sm.attach[c * 8 + (__float_as_int(qb.w) - sm.ffirst[c])] = (unsigned char)hb;
             }
         }
         __syncwarp();
