@@ -640,12 +640,14 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             const int rootc = __ffs((unsigned)((comp >> (8 * lane)) & 0xffull)) - 1;
             if (rootc != lane) { ea[4] = ffirst0 + lane; eb[4] = ffirst0 + rootc; }
         }
+        // These two look-ahead levels may come from L1 (ld.ca): a stale parent is still an ancestor-or-former-ancestor
+        // of the cell, i.e. a member of its set, which is all uf_unite needs; the hooks themselves use L2 (ld.cg/atomics).
 #pragma unroll
         for (int r = 0; r < 5; ++r)
-            if (ea[r] >= 0) { ea[r] = ld_cg(parent + ea[r]); eb[r] = ld_cg(parent + eb[r]); }
+            if (ea[r] >= 0) { ea[r] = __ldca(parent + ea[r]); eb[r] = __ldca(parent + eb[r]); }
 #pragma unroll
         for (int r = 0; r < 5; ++r)
-            if (ea[r] >= 0) { ea[r] = ld_cg(parent + ea[r]); eb[r] = ld_cg(parent + eb[r]); }
+            if (ea[r] >= 0) { ea[r] = __ldca(parent + ea[r]); eb[r] = __ldca(parent + eb[r]); }
 #pragma unroll
         for (int r = 0; r < 5; ++r)
             if (ea[r] >= 0 && ea[r] != eb[r]) uf_unite(parent, ea[r], eb[r]);  // ancestors stand in for the cells themselves

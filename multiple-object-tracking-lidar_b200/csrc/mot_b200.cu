@@ -582,6 +582,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->rws.status, h->rws.status_words));
         h->rws.err_flag = h->d_counts + CNT_FLAGS;
         if (const char* e = getenv("MOT_SORT_MODE")) h->rws.mode = atoi(e);
+        if (const char* e = getenv("MOT_SORT_BITS")) h->rws.digit_bits = std::min(RS_MAX_BITS, std::max(4, atoi(e)));
         CK(dalloc(&h->d_blk, (size_t)4 * 1024));
         CK(dalloc(&h->d_bbox, (size_t)8));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));

@@ -474,6 +474,7 @@ struct RadixWorkspace {
     size_t status_words = 0;
     int* err_flag = nullptr;     // device int (bit 1: look-back spin limit hit)
     int mode = 0;                // 0 = three kernels per pass (default: faster at 1M-8M pairs on B200), 1 = onesweep
+    int digit_bits = RS_MAX_BITS;  // widest digit of the three-kernel path (MOT_SORT_BITS, 4..10)
 };
 constexpr size_t rs_workspace_counters() { return (size_t)(1 << RS_MAX_BITS) * RS_MAX_GRID; }
 
@@ -529,7 +530,7 @@ inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, in
             return cur;
         }
     }
-    const int passes = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const int passes = (key_bits + ws.digit_bits - 1) / ws.digit_bits;
     const int base = key_bits / passes, rem = key_bits % passes;
     const Chunking ck = make_chunking(n, RS_TILE, RS_MAX_GRID);
     int cur = 0, shift = 0;

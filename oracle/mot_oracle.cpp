@@ -5,13 +5,21 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.  The
 // product library (libmot_b200.so) never links, loads or calls anything in oracle/.
 //
-// PARITY STATUS: "parity unpinned".  The reference ships no tests, golden vectors or fixtures for this
-// path and none of its translation units compile in this image (every TU needs
-// ROS, PCL, FLANN or Eigen, none of which are installed), so the oracle cannot be checked against the
-// reference's own outputs.  It is instead (1) restated line by line from the reference sources cited on
-// every function below, (2) cross-checked against an independent O(N^2) brute-force partition that uses
-// the identical fp32 predicate, and (3) cross-checked in tests against scipy (cKDTree, expm,
-// solve_discrete_are).  The one reference-owned fixture, map/sim_01.pgm, is used for removeStatic.
+// PARITY STATUS, per piece:
+//   pinned to the reference's own code -- removeStatic + yaw (orc_remove_static), getCentroid (orc_get_centroid), the
+//     IHGP constants and callIHGP (orc_ihgp_setup / orc_ihgp_step), and, in tracker_ref.py, the association / track
+//     lifecycle.  The reference ships no tests or golden vectors for this path, and its build needs
+//     ROS, PCL and Eigen (none installed); but its tracker and IHGP sources do compile, where they lie under
+//     /root/reference, against the stand-in headers of oracle/shim (oracle/Makefile target _ref, oracle/ref_harness.cpp).
+//     tests/test_ref_pin.py runs that build side by side with this file, and tests/golden/ref_vectors.npz holds its
+//     outputs (generator: tests/golden/make_ref_fixtures.py) for the places where /root/reference does not exist.
+//   "parity unpinned" -- the pieces that live in PCL, a third-party dependency outside the reference tree:
+//     EuclideanClusterExtraction over the FLANN KD-tree (orc_cluster_kdtree, orc_labels_*), VoxelGrid (orc_voxel_grid)
+//     and fromROSMsg (oracle.py).  Their published algorithms are restated and anchored on the reference's call sites;
+//     they are cross-checked against an independent O(N^2) brute-force partition using the identical fp32 predicate and,
+//     in tests, against scipy (cKDTree + connected components).  Inside oracle/_ref these same restatements stand in
+//     for PCL, so that build says nothing about them.
+//   The one reference-owned data fixture, map/sim_01.pgm, is used for removeStatic.
 //
 // Citations are relative to /root/reference:
 //   MOT.cpp = src/multiple_object_tracking_lidar.cpp

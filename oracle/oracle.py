@@ -1,8 +1,9 @@
 """ctypes front end of the CPU oracle (oracle/mot_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs.  The product package never imports this module.  Parity status: unpinned (see the
-header of mot_oracle.cpp and DESIGN.md).
+--impl reference legs.  The product package never imports this module.  Parity status: removeStatic, getCentroid and
+IHGP are pinned to the reference's own sources (oracle/_ref, tests/test_ref_pin.py); the PCL pieces (clustering,
+VoxelGrid, fromROSMsg) are restated and unpinned -- see the header of mot_oracle.cpp and DESIGN.md.
 """
 import ctypes as C
 import os

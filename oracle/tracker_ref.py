@@ -3,7 +3,9 @@
 Pure-Python loops (small cases only), each step citing the reference line it follows
 (MOT.cpp = src/multiple_object_tracking_lidar.cpp).  Floats are numpy scalars so that every operation rounds in the
 precision the C++ expression has (float members, double locals).  The IHGP call goes through the C++ oracle
-(orc_ihgp_step), one track at a time in this_objIDs order, exactly like callIHGP's loop.  Parity status: unpinned.
+(orc_ihgp_step), one track at a time in this_objIDs order, exactly like callIHGP's loop.  Parity status: pinned -- tests/test_ref_pin.py
+runs a 140-frame scenario through the reference's own cloudCallback (oracle/_ref) and through this class: ids, rings and
+published rows agree frame by frame (golden copy in tests/golden/ref_vectors.npz).
 """
 import numpy as np
 

@@ -1,7 +1,8 @@
 """CPU tests of the oracle itself: the restated reference path (KD-tree + BFS) against two independent
 implementations of the same fp32 predicate, hand-built known answers, scipy cross-checks and the one
-reference-owned fixture (map/sim_01).  The reference has no tests or golden vectors, so this
-is what pins the oracle -- parity stays "unpinned" with respect to real PCL."""
+reference-owned fixture (map/sim_01).  The reference has no tests or golden vectors; the pieces of
+the oracle that restate the reference's own code are pinned in tests/test_ref_pin.py, the PCL pieces tested here stay
+"unpinned" with respect to real PCL."""
 import os
 
 import numpy as np
