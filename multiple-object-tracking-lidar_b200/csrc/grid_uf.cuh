@@ -24,7 +24,7 @@
 namespace mot {
 
 // d_counts layout (ints)
-enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_EDGES = 7, CNT_HB = 8, CNT_N = 16 };
+enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_HB = 8, CNT_N = 16 };
 
 struct GridCodec {
     double minx, miny, minz, inv_e;
@@ -449,7 +449,7 @@ struct __align__(16) UfcWarpSmem {
 // warp-uniform register (8 x 8-bit masks), every adjacent neighbour cell remembers one child it touches, and at the
 // end ONE global edge per touched fine cell goes into the lock-free union-find (atomicMin hooking).
 // Tasks whose neighbourhood is too large for the tile are appended to the dense list for k_uf_dense.
-__global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restrict__ spts, const int* __restrict__ fc_start,
+__global__ void __launch_bounds__(UFC_THREADS, 5) k_uf_sparse(const float4* __restrict__ spts, const int* __restrict__ fc_start,
                                                             const int4* __restrict__ crec, const int* __restrict__ nbr,
                                                             int* __restrict__ d_counts, int* parent, float r2, int use_tma,
                                                             int* __restrict__ dense_list, int dense_cap) {
@@ -585,34 +585,34 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
                 }
             }
         }
-        // Fast chunks (64 points, two per lane): all of A's children are one component, so a hit lane only has to record
-        // ONE child it touches for its fine cell -- lanes of the same cell may race, every answer leads to the same root.
-        // Own-cell points (c == 0) need nothing any more.  Two points per lane share the broadcast LDS and the loop.
+        // Fast chunks (64 points, two per lane): all of A's children are one component, so a lane only has to find out
+        // WHETHER its point is within tol of any point of A (a running minimum of the squared distance, nothing else per
+        // test); its fine cell then attaches to child 0, which stands for the whole component.  Lanes of the same cell may
+        // race, every answer is the same.  Own-cell points (t < n_own) need nothing any more.
         for (; t0 < ptot; t0 += 64) {
             const int ta = t0 + lane, tb = t0 + 32 + lane;
             const float4 qa = ta < ptot ? sm.tile[ta] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);  // never within tol of anything
             const float4 qb = tb < ptot ? sm.tile[tb] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
-            int ha = -1, hb = -1;  // a child of A within tol of qa / qb
+            float da = 3.0e38f, db = 3.0e38f;  // one FMNMX per test, compared once at the end
 #pragma unroll 4
             for (int i = 0; i < n_own; ++i) {
                 const float4 pi = sm.tile[i];
-                const int child = __float_as_int(pi.w) - ffirst0;
-                if (dist2_exact(pi.x, pi.y, pi.z, qa.x, qa.y, qa.z) < r2) ha = child;
-                if (dist2_exact(pi.x, pi.y, pi.z, qb.x, qb.y, qb.z) < r2) hb = child;
+                da = fminf(da, dist2_exact(pi.x, pi.y, pi.z, qa.x, qa.y, qa.z));
+                db = fminf(db, dist2_exact(pi.x, pi.y, pi.z, qb.x, qb.y, qb.z));
             }
-            if (ha >= 0 && ta >= n_own) {
+            if (da < r2 && ta >= n_own) {
                 int c = 0;
 #pragma unroll
                 for (int k = 8; k > 0; k >>= 1)
                     if (c + k < UFC_CELLS && sm.coff[c + k] <= ta) c += k;
-                sm.attach[c * 8 + (__float_as_int(qa.w) - sm.ffirst[c])] = (unsigned char)ha;
+                sm.attach[c * 8 + (__float_as_int(qa.w) - sm.ffirst[c])] = 0;
             }
-            if (hb >= 0 && tb >= n_own) {
+            if (db < r2 && tb >= n_own) {
                 int c = 0;
 #pragma unroll
                 for (int k = 8; k > 0; k >>= 1)
                     if (c + k < UFC_CELLS && sm.coff[c + k] <= tb) c += k;
-                sm.attach[c * 8 + (__float_as_int(qb.w) - sm.ffirst[c])] = (unsigned char)hb;
+                sm.attach[c * 8 + (__float_as_int(qb.w) - sm.ffirst[c])] = 0;
             }
         }
         __syncwarp();
@@ -632,11 +632,7 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             }
         }
         ea[4] = -1; eb[4] = -1;
-        if (use_tma & 2) {  // timing aid (MOT_UF_TMA=3): drop every edge -- results are wrong, the sweep cost is isolated
-#pragma unroll
-            for (int r = 0; r < 4; ++r) ea[r] = -1;
-        }
-        if (lane < n_a && !(use_tma & 2)) {
+        if (lane < n_a) {
             const int rootc = __ffs((unsigned)((comp >> (8 * lane)) & 0xffull)) - 1;
             if (rootc != lane) { ea[4] = ffirst0 + lane; eb[4] = ffirst0 + rootc; }
         }
@@ -650,7 +646,13 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_sparse(const float4* __restr
             if (ea[r] >= 0) { ea[r] = __ldca(parent + ea[r]); eb[r] = __ldca(parent + eb[r]); }
 #pragma unroll
         for (int r = 0; r < 5; ++r)
-            if (ea[r] >= 0 && ea[r] != eb[r]) uf_unite(parent, ea[r], eb[r]);  // ancestors stand in for the cells themselves
+            if (ea[r] >= 0 && ea[r] != eb[r]) {
+                // the ancestors stand in for the cells themselves and are roots more often than not: hook straight away;
+                // atomicMin on a node that turns out not to be a root is what uf_unite's own retry path handles
+                const int hi = max(ea[r], eb[r]), lo = min(ea[r], eb[r]);
+                const int old = atomicMin(parent + hi, lo);
+                if (old != hi && old != lo) uf_unite(parent, old, lo);
+            }
         __syncwarp();
     }
 }

@@ -595,7 +595,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->prof.st = h->stream;
         CK(cudaFuncSetAttribute(k_uf_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(UFC_WARPS * sizeof(UfcWarpSmem))));
         if (const char* e = getenv("MOT_UF_MODE")) h->uf_mode = atoi(e);
-        if (const char* e = getenv("MOT_UF_TMA")) h->uf_tma = atoi(e);
+        if (const char* e = getenv("MOT_UF_TMA")) h->uf_tma = atoi(e) & 1;  // 0: plain loads instead of TMA staging (A/B)
         CK(rs_configure<uint32_t>());
         CK(rs_configure<uint64_t>());
         CK(cudaFuncSetAttribute(k_clusters_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMALL_SMEM));
