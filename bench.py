@@ -146,6 +146,8 @@ def run_b200(args, rank, world, local_rank):
     frame_offsets = np.arange(F + 1, dtype=np.int64) * n_pts
     d_all = torch.from_numpy(all_np).to(dev)          # the step's frames, resident in HBM
     S = max(1, args.streams)
+    # every handle has a host thread that spin-waits on its stream: leave a core per rank for the main thread and NCCL
+    S = max(1, min(S, (os.cpu_count() or 32) // max(world, 1) - 1))
     trks = [mot.Tracker(device=local_rank, max_points=F * n_pts, max_tracks=0) for _ in range(S)]
     for t_ in trks:
         t_.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
@@ -156,22 +158,28 @@ def run_b200(args, rank, world, local_rank):
     slot_rows = [0] * n_slots
     slot_full = [threading.Event() for _ in range(n_slots)]
     slot_free = [threading.Event() for _ in range(n_slots)]
+    # the steps' tables travel to rank 0 in blocks of GATHER_BLOCK steps: one collective per block (shard.gather_table_block)
+    GATHER_BLOCK = 8
+    agg = torch.zeros((GATHER_BLOCK, TABLE_ROWS + 1, 10), dtype=torch.float32, device=dev) if world > 1 else None
+    agg_all = [torch.zeros_like(agg) for _ in range(world)] if world > 1 and rank == 0 else None
 
     def step_device(gather, s=0, step_index=0):
         """One pass of the hot path over the step's batch of F frames (frame id rides in the voxel key).  With several
         GPUs the step's cluster table is left in a slot for the gather (done by the main thread in step order)."""
         tk = trks[s]
         tk.cluster_batch_device(d_all.data_ptr(), frame_offsets)
-        launches = tk.last_launches()
+        # the step's per-cluster table (count, mean, bbox) is part of the path at every N: written to a device slot
+        sl = step_index % n_slots
         if gather:
-            sl = step_index % n_slots
             slot_free[sl].wait()
             slot_free[sl].clear()
-            M, K, total = tk.result_counts()
-            k = min(K, TABLE_ROWS)
-            if k:
-                tk.lib.mot_result_fetch(tk.h, None, 0, None, 0, None, 0, slots[sl].data_ptr(), None, k)
-            slot_rows[sl] = k
+        M, K, total = tk.result_counts()
+        k = min(K, TABLE_ROWS)
+        if k:
+            tk.lib.mot_result_fetch(tk.h, None, 0, None, 0, None, 0, slots[sl].data_ptr(), None, k)
+        launches = tk.last_launches()  # the handle counts every kernel launched since the step began
+        slot_rows[sl] = k
+        if gather:
             slot_full[sl].set()
         return launches
 
@@ -198,9 +206,14 @@ def run_b200(args, rank, world, local_rank):
                 slot_full[sl].wait()
                 slot_full[sl].clear()
                 k = slot_rows[sl]
-                cnt = torch.tensor([k], dtype=torch.int64, device=dev)
-                shard.gather_tables(cnt, slots[sl][:k], device=dev)
+                j = i % GATHER_BLOCK
+                agg[j, 0, 0] = float(k)
+                if k:
+                    agg[j, 1:k + 1].copy_(slots[sl][:k], non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the slot may be refilled once its rows are in the block
                 slot_free[sl].set()
+                if j == GATHER_BLOCK - 1 or i == n_steps - 1:
+                    shard.gather_table_block(agg, agg_all)
         for t_ in th:
             t_.join()
         return sum(acc)
@@ -322,7 +335,9 @@ def run_b200(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(top["kernel"])
+            tj = json.load(f)
+        if tj.get("frames_per_launch") == args.frames:  # the capture is per launch: only valid for the same batch size
+            traffic = tj.get(top["kernel"])
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": round(top["gbs"] / peak, 4) if top["gbs"] else None, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": top["alg_bytes"], "avg_launch_us": top["avg_us"], "share_of_kernel_time": top["share"]}
@@ -438,7 +453,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=8, help="distinct frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
     ap.add_argument("--streams", type=int, default=4, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -83,6 +83,8 @@ struct mot_handle {
     RadixWorkspace rws;
     int* d_blk = nullptr;     // 4 * 1024 per-block counters
     int* d_counts = nullptr;  // CNT_N ints
+    cudaEvent_t sync_ev = nullptr;  // blocking-sync event (MOT_SYNC=block): host waits sleep instead of spinning
+    bool blocking_sync = false;
     int* d_bbox = nullptr;    // 8 ints
     uint64_t* d_ckeys[2] = {nullptr, nullptr};
     uint32_t* d_croots[2] = {nullptr, nullptr};
@@ -143,6 +145,16 @@ struct mot_handle {
 };
 
 // every kernel launch goes through LAUNCH: counts it and, when profiling is on, brackets it with an event pair
+// Host wait for the handle's stream.  Default: cudaStreamSynchronize (spins, lowest latency).  With MOT_SYNC=block the
+// wait goes through a cudaEventBlockingSync event, so the thread sleeps: for hosts that run more handles than cores
+// (several ranks x several streams per GPU on one node).
+static inline cudaError_t mot_sync(mot_handle* h) {
+    if (!h->blocking_sync) return cudaStreamSynchronize(h->stream);
+    cudaError_t e = cudaEventRecord(h->sync_ev, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->sync_ev);
+}
+
 #define LAUNCH(kid, ...)        \
     do {                        \
         h->prof.begin(kid);     \
@@ -303,7 +315,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     // ---- S1 ----
     CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     const int M = m_known >= 0 ? m_known : h->h_pinned[8 + CNT_M];
     h->res_cloud = cloud;
     h->res_M = M;
@@ -363,7 +375,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
                                                             h->max_size, kc, h->d_ckeys[0], h->d_croots[0], h->d_counts));
     // ---- S2 ----
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     const int K = h->h_pinned[8 + CNT_K];
     const int total = h->h_pinned[8 + CNT_TOTAL];
     h->res_K = K;
@@ -446,7 +458,7 @@ void fold_profile(mot_handle* h) {
 }
 
 int finish_timings(mot_handle* h) {
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
     cudaEventElapsedTime(&t01, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&t12, h->ev[1], h->ev[2]);
@@ -490,7 +502,7 @@ int fetch_result(mot_handle* h, float* kept, size_t kept_cap, int32_t* offs, siz
         if (!h->res_centroids) return fail(h, MOT_ERR_STATE, "centroids were not computed for the last result");
         CK(cudaMemcpyAsync(cent, h->d_centroids, (size_t)h->res_K * 16, cudaMemcpyDefault, st));
     }
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     return MOT_OK;
 }
 
@@ -545,6 +557,8 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(cudaGetDeviceProperties(&prop, device));
         h->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        if (const char* e = getenv("MOT_SYNC")) h->blocking_sync = std::string(e) == "block";
+        CK(cudaEventCreateWithFlags(&h->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         const size_t n = max_points;
         CK(dalloc(&h->d_in, n));
         CK(dalloc(&h->d_pts, n));
@@ -633,7 +647,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
 int mot_destroy(mot_handle* h) {
     if (!h) return MOT_ERR_INVALID;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) mot_sync(h);
     void* ptrs[] = {h->d_in, h->d_pts, h->d_spts, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_ckeys[0], h->d_ckeys[1],
                     h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
                     h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->rws.ghist, h->rws.status, h->d_blk,
@@ -649,6 +663,7 @@ int mot_destroy(mot_handle* h) {
     for (auto& e : h->timer_ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->prof.pool) cudaEventDestroy(e);
+    if (h->sync_ev) cudaEventDestroy(h->sync_ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOT_OK;
@@ -680,7 +695,7 @@ int mot_set_map(mot_handle* h, const int8_t* occ, int width, int height, float r
         k_build_blocked_bitmap<<<(unsigned)((cells + 255) / 256), 256, 0, h->stream>>>(d_occ, width, height, static_tolerance, h->d_bits);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = mot_sync(h);
     cudaFree(d_occ);
     if (e != cudaSuccess) { h->err = std::string("mot_set_map: ") + cudaGetErrorString(e); return MOT_ERR_CUDA; }
     // yaw exactly as quaternion2eularYaw (MOT.cpp:1013-1023): double atan2 returned through a float; then the
@@ -724,13 +739,13 @@ int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xy
     rc = enqueue_remove_static(h, h->d_in, (int)n);
     if (rc != MOT_OK) return rc;
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     const size_t M = (size_t)h->h_pinned[8 + CNT_M];
     *m = M;
     if (out_xyz16) {
         if (out_capacity < M) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
         if (M) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, M * 16, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(mot_sync(h));
     }
     return MOT_OK;
 }
@@ -746,7 +761,7 @@ static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     LAUNCH(KID_BBOX, k_bbox<<<grid, 256, 0, st>>>(d_src, n, h->d_bbox));
     CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     if (h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
     VoxelParams vp{};
     const float leaf[3] = {lx, ly, lz};
@@ -768,7 +783,7 @@ static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx
     LAUNCH(KID_SEG_COUNT, k_seg_count<<<ck.grid, 256, 0, st>>>(keys[sb], n, ck.chunk, h->d_blk));
     LAUNCH(KID_SEG_WRITE, k_seg_write<<<ck.grid, 256, 0, st>>>(keys[sb], n, ck.chunk, h->d_blk, h->d_cl_offsets, h->d_counts + CNT_K));
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     const int V = h->h_pinned[8 + CNT_K];
     int rc = ensure_tables(h, (size_t)V, 0);
     if (rc != MOT_OK) return rc;
@@ -800,7 +815,7 @@ int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, fl
         if (out_capacity < (size_t)V) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
         if (V) CK(cudaMemcpyAsync(out_xyz16, h->d_pts, (size_t)V * 16, cudaMemcpyDefault, h->stream));
     }
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     fold_profile(h);
     return MOT_OK;
 }
@@ -835,7 +850,7 @@ int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, 
     if (drop_nonfinite) {
         LAUNCH(KID_PC2_COMPACT, k_pc2_compact<<<ck.grid, 256, 0, st>>>(h->d_in, n, ck.chunk, h->d_blk, h->d_pts, h->d_counts + CNT_M));
         CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(mot_sync(h));
         M = (size_t)h->h_pinned[8 + CNT_M];
         result = h->d_pts;
     }
@@ -845,7 +860,7 @@ int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, 
         if (out_capacity < M) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
         if (M) CK(cudaMemcpyAsync(out_xyz16, result, M * 16, cudaMemcpyDefault, st));
     }
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     fold_profile(h);
     return MOT_OK;
 }
@@ -974,7 +989,7 @@ int mot_result_labels(mot_handle* h, int32_t* labels, size_t capacity) {
     if (capacity < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "labels buffer too small");
     CK(cudaSetDevice(h->device));
     if (h->res_M) CK(cudaMemcpyAsync(labels, h->d_labels, (size_t)h->res_M * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     return MOT_OK;
 }
 
@@ -1043,7 +1058,7 @@ static int batch_setup(mot_handle* h, const int64_t* frame_offsets, int n_frames
     int rc = reset_frame_state(h);
     if (rc != MOT_OK) return rc;
     CK(cudaMemcpyAsync(h->d_frame_offsets, fo.data(), fo.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));  // fo is a stack-owned pageable buffer
+    CK(mot_sync(h));  // fo is a stack-owned pageable buffer
     return MOT_OK;
 }
 
@@ -1203,7 +1218,7 @@ static int ihgp_step_impl(mot_handle* h, const float* rings, int n_tracks, const
     CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (obstacles) CK(cudaMemcpyAsync(obstacles, h->d_obstacles, (size_t)n_tracks * sizeof(ObstacleRow), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     fold_profile(h);
     return MOT_OK;
 }
@@ -1215,7 +1230,7 @@ int mot_tracks_reset(mot_handle* h) {
     if (h->max_tracks == 0) return fail(h, MOT_ERR_CAPACITY, "handle was created with max_tracks = 0");
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_trk_meta, 0, TM_N * sizeof(int), h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     h->trk_cur = 0; h->trk_spin = 0; h->trk_n = 0; h->trk_first = true;
     return MOT_OK;
 }
@@ -1253,14 +1268,14 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
                                                                   h->d_trk_rings[cur], h->d_trk_m[cur], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids,
                                                                   h->d_ent_slot, h->d_ent_occ));
     CK(cudaMemcpyAsync(h->h_pinned + 32, h->d_trk_meta, TM_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     h->trk_n = h->h_pinned[32 + TM_NTRACKS];
     if (n_tracks) *n_tracks = h->trk_n;
     if (h->h_pinned[32 + TM_OVERFLOW]) return fail(h, MOT_ERR_CAPACITY, "track table full (max_tracks)");
     if (this_obj_ids) CK(cudaMemcpyAsync(this_obj_ids, h->d_ent_ids, (size_t)K * sizeof(int), cudaMemcpyDefault, st));
     if (h->trk_first) {
         h->trk_first = false;
-        CK(cudaStreamSynchronize(st));
+        CK(mot_sync(h));
         fold_profile(h);
         return MOT_OK;
     }
@@ -1287,7 +1302,7 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
         CK(cudaMemcpyAsync(h->h_pinned + 32, h->d_trk_meta, TM_N * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
+    CK(mot_sync(h));
     h->trk_n = h->h_pinned[32 + TM_NTRACKS];
     if (n_tracks) *n_tracks = h->trk_n;
     if (produced) *produced = 1;
@@ -1305,7 +1320,7 @@ int mot_tracks_get(mot_handle* h, int32_t* ids, float* rings, double* m_state, s
     if (ids) CK(cudaMemcpyAsync(ids, h->d_trk_ids[cur], (size_t)h->trk_n * sizeof(int), cudaMemcpyDefault, h->stream));
     if (rings) CK(cudaMemcpyAsync(rings, h->d_trk_rings[cur], (size_t)h->trk_n * h->trk_L * 16, cudaMemcpyDefault, h->stream));
     if (m_state) CK(cudaMemcpyAsync(m_state, h->d_trk_m[cur], (size_t)h->trk_n * 4 * sizeof(double), cudaMemcpyDefault, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(mot_sync(h));
     return MOT_OK;
 }
 

@@ -48,3 +48,24 @@ def gather_tables(counts, payload, device=None, group=None):
     if rank != 0:
         return None
     return [(all_counts[r], all_payload[r][: int(all_rows[r].item())]) for r in range(world)]
+
+
+def gather_table_block(block, gather_list=None, group=None):
+    """One collective for a whole block of steps: `block` is a float32 tensor [G, rows + 1, 10] -- per step, row 0 holds the
+    number of valid table rows in column 0, the table follows -- of the same shape on every rank.  Rank 0 passes
+    gather_list (world tensors shaped like block) and finds every rank's block there afterwards.  Used by bench.py so
+    that the exchange costs one NCCL launch per G steps instead of three per step (a collective's kernel has to wait
+    for SM space behind the frame kernels, so few large gathers beat many small ones)."""
+    import torch.distributed as dist
+
+    dist.gather(block, gather_list if dist.get_rank(group) == 0 else None, dst=0, group=group)
+    return gather_list
+
+
+def unpack_table_block(block):
+    """Inverse of the packing above for one rank's block: list over steps of [K, 10] tensors."""
+    out = []
+    for j in range(block.shape[0]):
+        k = int(block[j, 0, 0].item())
+        out.append(block[j, 1:k + 1])
+    return out

@@ -38,9 +38,18 @@ def _worker(rank, world, port, q):
     tables = [rng.random((k, 10), dtype=np.float32) for k in ((3, 0, 5) if rank == 0 else (2, 7, 1))]
     counts, payload = shard.pack_tables(tables)
     res = shard.gather_tables(torch.from_numpy(counts), torch.from_numpy(payload), device=torch.device("cpu"))
+    # block-wise exchange used by bench.py: G steps per collective, row 0 of every step carries its row count
+    G, rows = 3, 8
+    block = torch.zeros((G, rows + 1, 10))
+    for j, t in enumerate(tables):
+        block[j, 0, 0] = float(len(t))
+        block[j, 1:len(t) + 1] = torch.from_numpy(t)
+    gl = [torch.zeros_like(block) for _ in range(world)] if rank == 0 else None
+    shard.gather_table_block(block, gl)
     if rank == 0:
         out = [(c.numpy().tolist(), p.numpy()) for c, p in res]
-        q.put((out, payload))
+        blocks = [[t.numpy() for t in shard.unpack_table_block(b)] for b in gl]
+        q.put((out, payload, blocks))
     else:
         assert res is None
         q.put(("payload", rank, payload))
@@ -65,7 +74,9 @@ def test_gather_tables_gloo_world2():
         assert p.exitcode == 0
     rank0 = [g for g in got if g[0] != "payload"][0]
     rank1 = [g for g in got if g[0] == "payload"][0]
-    out, payload0 = rank0
+    out, payload0, blocks = rank0
+    for r, pay in ((0, payload0), (1, rank1[2])):   # the block gather delivers the same tables, step by step
+        assert [len(t) for t in blocks[r]] == out[r][0] and np.array_equal(np.concatenate(blocks[r]), pay)
     assert out[0][0] == [3, 0, 5] and out[1][0] == [2, 7, 1]
     assert np.array_equal(out[0][1], payload0) and np.array_equal(out[1][1], rank1[2])
     assert out[1][1].shape == (10, 10)
