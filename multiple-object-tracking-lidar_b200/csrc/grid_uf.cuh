@@ -126,6 +126,10 @@ __device__ __forceinline__ int hash_find(const KT* __restrict__ hkeys, const int
 // ---- K3: reorder + cell tables ---------------------------------------------------------------------------
 constexpr int CELL_THREADS = 256;
 constexpr int CELL_MAX_GRID = 592;
+// k_cells_count / k_cells_write run with many more blocks than fit on the GPU at once: blocks start in index order, so the
+// resident ones work on one neighbourhood of the sorted array and the random 16-byte point gathers stay inside an L2-sized
+// window of the input (a batch of frames is far larger than L2; 592 chunks covering everything at once measured 1.55x slower)
+constexpr int CELLW_MAX_GRID = 8192;
 
 // counts[0][b] = fine-cell heads in block b's chunk, counts[1][b] = coarse-cell heads.
 template <typename KT>
@@ -158,8 +162,25 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restri
 // kernel reads log2(size) from d_counts[CNT_HB].
 template <typename KT>
 __global__ void __launch_bounds__(256) k_hash_clear(const int* __restrict__ counts, int n_blocks, int hb_max, KT* __restrict__ hkeys,
-                                                     int* __restrict__ d_counts) {
+                                                     int* __restrict__ d_counts, int* __restrict__ prefix) {
     __shared__ int scratch[36];
+    if (blockIdx.x == 0) {
+        // exclusive prefixes of the per-block head counts (fine cells, then coarse cells) for k_cells_write
+        const int per = (n_blocks + 255) / 256;
+        const int i0 = threadIdx.x * per, i1 = min(n_blocks, i0 + per);
+        for (int arr = 0; arr < 2; ++arr) {
+            const int* c = counts + arr * n_blocks;
+            int* o = prefix + arr * n_blocks;
+            int sum = 0;
+            for (int i = i0; i < i1; ++i) sum += c[i];
+            int total;
+            int run = block_exclusive_scan(sum, scratch, &total);
+            for (int i = i0; i < i1; ++i) {
+                o[i] = run;
+                run += c[i];
+            }
+        }
+    }
     const int n_coarse = block_prefix_of(counts + n_blocks, n_blocks, scratch);
     int hb = 4;
     while (hb < hb_max && (1ll << hb) < 4ll * n_coarse) ++hb;
@@ -185,8 +206,8 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
         hmask = (1u << hb) - 1u;
         hshift = 32 - hb;
     }
-    int fbase = block_prefix_of(counts, blockIdx.x, scratch);
-    int cbase = block_prefix_of(counts + gridDim.x, blockIdx.x, scratch);
+    int fbase = counts[2 * gridDim.x + blockIdx.x];  // exclusive prefixes written by k_hash_clear behind the two count rows
+    int cbase = counts[3 * gridDim.x + blockIdx.x];
     const int begin = blockIdx.x * chunk, end = min(m, begin + chunk);
     for (int tb = begin; tb < end; tb += CELL_THREADS) {
         const int j = tb + threadIdx.x;

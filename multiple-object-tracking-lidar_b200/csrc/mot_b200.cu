@@ -81,7 +81,7 @@ struct mot_handle {
     int* d_hvals = nullptr;
     size_t hash_capacity = 0;
     RadixWorkspace rws;
-    int* d_blk = nullptr;     // 4 * 1024 per-block counters
+    int* d_blk = nullptr;     // 32 * 1024 per-block counters (k_cells_*: 4 rows of up to CELLW_MAX_GRID)
     int* d_counts = nullptr;  // CNT_N ints
     cudaEvent_t sync_ev = nullptr;  // blocking-sync event (MOT_SYNC=block): host waits sleep instead of spinning
     bool blocking_sync = false;
@@ -255,9 +255,10 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     while (((size_t)1 << hb_max) > h->hash_capacity) --hb_max;  // capacity holds >= 2 slots per point: load <= 0.5 always
     const unsigned hmask = 0;  // both are read from d_counts[CNT_HB] inside the kernels
     const int hshift = 0;
-    const Chunking ck = make_chunking(M, CELL_THREADS, CELL_MAX_GRID);
+    const Chunking ck = make_chunking(M, CELL_THREADS, CELLW_MAX_GRID);
     LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, M, ck.chunk, h->d_blk));
-    LAUNCH(KID_HASH_CLEAR, k_hash_clear<KT><<<h->num_sms * 2, 256, 0, st>>>(h->d_blk, ck.grid, hb_max, reinterpret_cast<KT*>(h->d_hkeys), h->d_counts));
+    LAUNCH(KID_HASH_CLEAR, k_hash_clear<KT><<<h->num_sms * 2, 256, 0, st>>>(h->d_blk, ck.grid, hb_max, reinterpret_cast<KT*>(h->d_hkeys), h->d_counts,
+                                                                             h->d_blk + 2 * ck.grid));
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
@@ -597,7 +598,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->rws.err_flag = h->d_counts + CNT_FLAGS;
         if (const char* e = getenv("MOT_SORT_MODE")) h->rws.mode = atoi(e);
         if (const char* e = getenv("MOT_SORT_BITS")) h->rws.digit_bits = std::min(RS_MAX_BITS, std::max(4, atoi(e)));
-        CK(dalloc(&h->d_blk, (size_t)4 * 1024));
+        CK(dalloc(&h->d_blk, (size_t)32 * 1024));
         CK(dalloc(&h->d_bbox, (size_t)8));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));
         h->frame_capacity = 4096;

@@ -30,5 +30,5 @@ for _ in range(reps):
 prof = trk.profile()
 tot = sum(ms for ms, c in prof.values()) / reps
 print(trk.result_counts(), f"kernel time per batch {tot * 1e3:.1f} us")
-for k, (ms, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]:
+for k, (ms, c) in sorted(prof.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("TOPK", "6"))]:
     print(f"{k:28s} {ms / c * 1e3:10.1f} us x{c}")
