@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_count(const KT* __restri
     }
 }
 
-// The coarse-cell hash is sized on the device from the head count k_cells_count just produced (4 slots per occupied
-// coarse cell, so probes stay ~1 and the table of a LiDAR frame stays L2 resident) and cleared here; every later
-// kernel reads log2(size) from d_counts[CNT_HB].
+// The coarse-cell hash is sized on the device from the head count k_cells_count just produced (2-4 slots per occupied
+// coarse cell: short probe chains, and the table of a batch of LiDAR frames stays L2 resident -- 4-8 slots measured
+// slower) and cleared here; every later kernel reads log2(size) from d_counts[CNT_HB].
 template <typename KT>
 __global__ void __launch_bounds__(256) k_hash_clear(const int* __restrict__ counts, int n_blocks, int hb_max, KT* __restrict__ hkeys,
                                                      int* __restrict__ d_counts, int* __restrict__ prefix) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_hash_clear(const int* __restrict__ coun
     }
     const int n_coarse = block_prefix_of(counts + n_blocks, n_blocks, scratch);
     int hb = 4;
-    while (hb < hb_max && (1ll << hb) < 4ll * n_coarse) ++hb;
+    while (hb < hb_max && (1ll << hb) < 2ll * n_coarse) ++hb;
     if (blockIdx.x == 0 && threadIdx.x == 0) d_counts[CNT_HB] = hb;
     const size_t size = (size_t)1 << hb;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x) hkeys[i] = ~(KT)0;
