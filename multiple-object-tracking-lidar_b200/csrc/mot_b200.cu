@@ -85,6 +85,7 @@ struct mot_handle {
     int* d_counts = nullptr;  // CNT_N ints
     cudaEvent_t sync_ev = nullptr;  // blocking-sync event (MOT_SYNC=block): host waits sleep instead of spinning
     bool blocking_sync = false;
+    int uf_blocks_per_sm = 5;  // resident CTAs of k_uf_sparse per SM (MOT_UF_BLOCKS; fewer leaves room for other streams' kernels)
     int* d_bbox = nullptr;    // 8 ints
     uint64_t* d_ckeys[2] = {nullptr, nullptr};
     uint32_t* d_croots[2] = {nullptr, nullptr};
@@ -277,7 +278,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
                                                                            reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift, g,
                                                                            h->d_crec, h->d_nbr));
         int cgrid = (M + UFC_WARPS - 1) / UFC_WARPS;
-        if (cgrid > h->num_sms * 5) cgrid = h->num_sms * 5;
+        if (cgrid > h->num_sms * h->uf_blocks_per_sm) cgrid = h->num_sms * h->uf_blocks_per_sm;
         const size_t usm = UFC_WARPS * sizeof(UfcWarpSmem);
         LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                            h->uf_tma, h->d_dense_list, h->dense_cap));
@@ -559,6 +560,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         if (const char* e = getenv("MOT_SYNC")) h->blocking_sync = std::string(e) == "block";
+        if (const char* e = getenv("MOT_UF_BLOCKS")) h->uf_blocks_per_sm = std::min(5, std::max(1, atoi(e)));
         CK(cudaEventCreateWithFlags(&h->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         const size_t n = max_points;
         CK(dalloc(&h->d_in, n));

@@ -2,6 +2,8 @@
 
 Bars: bit-exact for the removeStatic output, the cluster partition and the CSR arrays (integer / index work);
 rtol 1e-5 for centroids, bbox/mean and IHGP states (north_star's fp32 tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -366,7 +368,7 @@ def test_tracks_association_lifecycle(mot, oracle, seed, L):
     t.close()
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("MOT_FUZZ_SEEDS", "12"))))
 def test_fuzz_partition_vs_oracle(trk, oracle, seed):
     # randomised differential test: mixtures of dense blobs, planes, lines and uniform noise at random scales / tolerances;
     # exercises sparse and dense union-find tasks, 1-3 radix passes, empty / tiny clusters, min/max filters
