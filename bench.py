@@ -454,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
-    ap.add_argument("--streams", type=int, default=4, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
+    ap.add_argument("--streams", type=int, default=6, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -85,6 +85,11 @@ struct mot_handle {
     int* d_counts = nullptr;  // CNT_N ints
     cudaEvent_t sync_ev = nullptr;  // blocking-sync event (MOT_SYNC=block): host waits sleep instead of spinning
     bool blocking_sync = false;
+    // The union-find kernels (latency bound, they hold every SM for ~2 ms per batch) run on a lowest-priority side stream
+    // and everything else on a highest-priority one: when several handles share the GPU, the bandwidth-bound kernels of
+    // the other handles are placed on the SMs first instead of queueing behind a union-find launch (MOT_UF_PRIO=0: off).
+    cudaStream_t uf_stream = nullptr;
+    cudaEvent_t ev_uf[2] = {nullptr, nullptr};
     int uf_blocks_per_sm = 5;  // resident CTAs of k_uf_sparse per SM (MOT_UF_BLOCKS; fewer leaves room for other streams' kernels)
     int* d_bbox = nullptr;    // 8 ints
     uint64_t* d_ckeys[2] = {nullptr, nullptr};
@@ -280,6 +285,13 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
         int cgrid = (M + UFC_WARPS - 1) / UFC_WARPS;
         if (cgrid > h->num_sms * h->uf_blocks_per_sm) cgrid = h->num_sms * h->uf_blocks_per_sm;
         const size_t usm = UFC_WARPS * sizeof(UfcWarpSmem);
+        const cudaStream_t main_st = st;
+        const bool side = h->uf_stream && !h->prof.on;
+        if (side) {
+            CK(cudaEventRecord(h->ev_uf[0], main_st));
+            CK(cudaStreamWaitEvent(h->uf_stream, h->ev_uf[0], 0));
+            st = h->uf_stream;
+        }
         LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                            h->uf_tma, h->d_dense_list, h->dense_cap));
         int dgrid = cgrid < h->num_sms * 8 ? cgrid : h->num_sms * 8;
@@ -289,6 +301,11 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
         LAUNCH(KID_UF_DENSE, k_uf_dense<2><<<dgrid, UFC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                            h->d_dense_list, h->dense_cap));
         LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+        if (side) {
+            CK(cudaEventRecord(h->ev_uf[1], st));
+            st = main_st;
+            CK(cudaStreamWaitEvent(st, h->ev_uf[1], 0));
+        }
     } else {
         LAUNCH(KID_UF1, k_uf_pairs<KT, 1><<<uf_grid, UF_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first,
                                                                           reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
@@ -561,6 +578,18 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         if (const char* e = getenv("MOT_SYNC")) h->blocking_sync = std::string(e) == "block";
         if (const char* e = getenv("MOT_UF_BLOCKS")) h->uf_blocks_per_sm = std::min(5, std::max(1, atoi(e)));
+        {
+            const char* e = getenv("MOT_UF_PRIO");  // default on; MOT_UF_PRIO=0 keeps everything on one stream
+            if (!e || atoi(e) != 0) {
+                int least = 0, greatest = 0;
+                CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                CK(cudaStreamDestroy(h->stream));
+                CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+                CK(cudaStreamCreateWithPriority(&h->uf_stream, cudaStreamNonBlocking, least));
+                CK(cudaEventCreateWithFlags(&h->ev_uf[0], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&h->ev_uf[1], cudaEventDisableTiming));
+            }
+        }
         CK(cudaEventCreateWithFlags(&h->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
         const size_t n = max_points;
         CK(dalloc(&h->d_in, n));
@@ -667,6 +696,8 @@ int mot_destroy(mot_handle* h) {
         if (e) cudaEventDestroy(e);
     for (auto& e : h->prof.pool) cudaEventDestroy(e);
     if (h->sync_ev) cudaEventDestroy(h->sync_ev);
+    for (cudaEvent_t e : h->ev_uf) if (e) cudaEventDestroy(e);
+    if (h->uf_stream) cudaStreamDestroy(h->uf_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return MOT_OK;
