@@ -449,6 +449,9 @@ constexpr int UFC_WARPS = UFC_THREADS / 32;
 constexpr int UFC_TILE_PTS = 256;   // points of the forward neighbourhood staged per warp (4 KB)
 constexpr int UFC_CELLS = 14;       // half stencil: the coarse cell itself + its 13 "forward" neighbours
 constexpr int UFC_NODES = UFC_CELLS * 8;
+#ifndef UFC_MIN_BLOCKS
+#define UFC_MIN_BLOCKS 5
+#endif
 constexpr int UFC_BRUTE_TESTS = 4096;  // brute-force sweep only while (own points) x (neighbourhood points) stays below this
 struct __align__(16) UfcWarpSmem {
     float4 tile[UFC_TILE_PTS];
@@ -470,7 +473,7 @@ struct __align__(16) UfcWarpSmem {
 // warp-uniform register (8 x 8-bit masks), every adjacent neighbour cell remembers one child it touches, and at the
 // end ONE global edge per touched fine cell goes into the lock-free union-find (atomicMin hooking).
 // Tasks whose neighbourhood is too large for the tile are appended to the dense list for k_uf_dense.
-__global__ void __launch_bounds__(UFC_THREADS, 5) k_uf_sparse(const float4* __restrict__ spts, const int* __restrict__ fc_start,
+__global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse(const float4* __restrict__ spts, const int* __restrict__ fc_start,
                                                             const int4* __restrict__ crec, const int* __restrict__ nbr,
                                                             int* __restrict__ d_counts, int* parent, float r2, int use_tma,
                                                             int* __restrict__ dense_list, int dense_cap) {

@@ -577,7 +577,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         if (const char* e = getenv("MOT_SYNC")) h->blocking_sync = std::string(e) == "block";
-        if (const char* e = getenv("MOT_UF_BLOCKS")) h->uf_blocks_per_sm = std::min(5, std::max(1, atoi(e)));
+        if (const char* e = getenv("MOT_UF_BLOCKS")) h->uf_blocks_per_sm = std::min(8, std::max(1, atoi(e)));
         {
             const char* e = getenv("MOT_UF_PRIO");  // default on; MOT_UF_PRIO=0 keeps everything on one stream
             if (!e || atoi(e) != 0) {
