@@ -14,10 +14,12 @@
 // of points per cell on a LiDAR-sampled surface) near linear instead of quadratic in cell occupancy.
 //
 // Key layout (low to high bits): 3 fine bits (fz fy fx) | cx | cy | cz | frame id (batch mode).
-// Points are radix sorted by key, so the fine cells of one coarse cell are contiguous; the open-addressing
-// hash maps a coarse key to the index of its first fine cell.  A warp owns one fine cell A: 27 lanes probe
-// the 27 coarse neighbours, the (<= 216) candidate fine cells are compacted into a per-warp list, small
-// cell pairs are searched by one lane each, large ones cooperatively by the whole warp with shuffles.
+// Points are radix sorted by key, so the fine cells of one coarse cell are contiguous; an open-addressing hash maps a
+// coarse key to its coarse-cell index, and k_coarse_records resolves every coarse cell's forward half stencil (13
+// neighbours) into one 16-int row.  Union-find work is dealt per coarse cell: k_uf_sparse stages the cell's forward
+// neighbourhood in shared memory (TMA) and sweeps it by brute force with the exact predicate; neighbourhoods too large
+// for the tile go to k_uf_dense, which looks for one witness pair per (fine cell, fine cell) candidate.  The first
+// generation (k_uf_pairs: a warp per fine cell probing 27 coarse neighbours) is kept selectable for A/B (MOT_UF_MODE=0).
 #pragma once
 #include "common.cuh"
 
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(UF_THREADS) k_uf_pairs(const KT* __restrict__ 
     }
 }
 
-// ---- K4 (v2): one warp per COARSE cell, points staged by TMA, local union-find in shared memory ----------------
+// ---- K4: one warp per COARSE cell (records + half stencil, then k_uf_sparse / k_uf_dense) ----------------------------
 //
 // Record of an occupied coarse cell: x = first sorted point, y = point count, z = first fine cell, w = bit mask
 // of its occupied fine children (child code = fz<<2 | fy<<1 | fx).  The fine children are consecutive fine-cell
