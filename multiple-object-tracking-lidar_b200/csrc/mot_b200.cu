@@ -1,19 +1,23 @@
 // mot_b200.cu -- host side of libmot_b200.so: the C ABI declared in include/mot_b200.h and the per-frame
 // launch sequence.  C++ host code calling hand-written sm_100a kernels; no PyTorch, no CPU fallback.
 //
-// Frame pipeline (one CUDA stream per handle, two host round trips of 32 bytes each):
+// Frame pipeline (one CUDA stream per handle -- plus a low-priority side stream for the K4 kernels -- and two host round
+// trips of 32 bytes each):
 //   K0  k_rs_count / k_rs_compact     removeStatic: bit lookup + stable compaction (+ bbox of kept points)
 //   --  S1: read M and the bounding box (sizes the grid: key width, radix passes, hash table)
 //   K1  k_cell_keys                   fp64 cell coordinates -> voxel key
 //   K2  k_rs_hist/scan/scatter        LSD radix sort of (key, index), ceil(bits/10) passes
-//   K3  k_cells_count / k_cells_write reorder to sorted SoA, fine/coarse cell tables, coarse-cell hash
-//   K4  k_uf_pairs<1>, <2>            27-coarse-cell witness search + atomicMin hooking (rings 1 and 2)
-//   K5  k_uf_flatten                  pointer jumping
+//   K3  k_cells_count / k_hash_clear / k_cells_write   reorder to sorted SoA, fine/coarse cell tables, coarse-cell hash
+//   K4  k_coarse_records              per coarse cell: record + resolved forward half stencil (13 neighbours)
+//       k_uf_sparse                   warp per coarse cell: TMA-staged neighbourhood, exact brute-force sweep, atomicMin hooking
+//       k_uf_dense<1>, <2>            neighbourhoods too large for the tile: witness search per fine-cell pair (rings 1, 2)
+//       (MOT_UF_MODE=0: k_uf_pairs<1>, <2>, the first-generation warp-per-fine-cell kernels)
+//   K5  k_uf_flatten                  pointer jumping (in place between the dense rings, then into root[])
 //   K6  k_comp_accumulate/k_kept_list component sizes, [min,max] filter
 //   --  S2: read K (sizes the cluster sort and the CSR partition)
 //       k_clusters_small | radix64    order clusters (size desc, min index asc), CSR offsets
 //       k_point_rank + radix32        stable partition of point indices by cluster rank = CSR indices
-//   K7  k_cluster_stats               segmented reduction: count / mean / bbox
+//   K7  k_stats_init/accumulate/finalize  point-parallel segmented reduction: count / mean / bbox
 //   K8  k_farthest_pair/k_circumcentre  the reference's getCentroid
 //   K9  k_ihgp_step                   batched track filter (separate entry point)
 #include <cmath>
