@@ -20,6 +20,8 @@
 //   K7  k_stats_init/accumulate/finalize  point-parallel segmented reduction: count / mean / bbox
 //   K8  k_farthest_pair/k_circumcentre  the reference's getCentroid
 //   K9  k_ihgp_step                   batched track filter (separate entry point)
+#include <sched.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -88,7 +90,7 @@ struct mot_handle {
     int* d_blk = nullptr;     // 32 * 1024 per-block counters (k_cells_*: 4 rows of up to CELLW_MAX_GRID)
     int* d_counts = nullptr;  // CNT_N ints
     cudaEvent_t sync_ev = nullptr;  // blocking-sync event (MOT_SYNC=block): host waits sleep instead of spinning
-    bool blocking_sync = false;
+    int sync_mode = 0;  // 0 spin, 1 yield, 2 block (MOT_SYNC)
     // The union-find kernels (latency bound, they hold every SM for ~2 ms per batch) run on a lowest-priority side stream
     // and everything else on a highest-priority one: when several handles share the GPU, the bandwidth-bound kernels of
     // the other handles are placed on the SMs first instead of queueing behind a union-find launch (MOT_UF_PRIO=0: off).
@@ -155,14 +157,16 @@ struct mot_handle {
 };
 
 // every kernel launch goes through LAUNCH: counts it and, when profiling is on, brackets it with an event pair
-// Host wait for the handle's stream.  Default: cudaStreamSynchronize (spins, lowest latency).  With MOT_SYNC=block the
-// wait goes through a cudaEventBlockingSync event, so the thread sleeps: for hosts that run more handles than cores
-// (several ranks x several streams per GPU on one node).
+// Host wait for the handle's stream.  Default: cudaStreamSynchronize (spins, lowest latency).  MOT_SYNC=yield polls an
+// event and gives the core away between polls -- for hosts that run more handles than cores (several ranks x several
+// streams per GPU on one node); MOT_SYNC=block sleeps on a cudaEventBlockingSync event (slowest to wake up).
 static inline cudaError_t mot_sync(mot_handle* h) {
-    if (!h->blocking_sync) return cudaStreamSynchronize(h->stream);
+    if (h->sync_mode == 0) return cudaStreamSynchronize(h->stream);
     cudaError_t e = cudaEventRecord(h->sync_ev, h->stream);
     if (e != cudaSuccess) return e;
-    return cudaEventSynchronize(h->sync_ev);
+    if (h->sync_mode == 2) return cudaEventSynchronize(h->sync_ev);
+    while ((e = cudaEventQuery(h->sync_ev)) == cudaErrorNotReady) sched_yield();
+    return e;
 }
 
 #define LAUNCH(kid, ...)        \
@@ -580,7 +584,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(cudaGetDeviceProperties(&prop, device));
         h->num_sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        if (const char* e = getenv("MOT_SYNC")) h->blocking_sync = std::string(e) == "block";
+        if (const char* e = getenv("MOT_SYNC")) h->sync_mode = std::string(e) == "block" ? 2 : (std::string(e) == "yield" ? 1 : 0);
         if (const char* e = getenv("MOT_UF_BLOCKS")) h->uf_blocks_per_sm = std::min(8, std::max(1, atoi(e)));
         {
             const char* e = getenv("MOT_UF_PRIO");  // default on; MOT_UF_PRIO=0 keeps everything on one stream
@@ -594,7 +598,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
                 CK(cudaEventCreateWithFlags(&h->ev_uf[1], cudaEventDisableTiming));
             }
         }
-        CK(cudaEventCreateWithFlags(&h->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->sync_ev, (h->sync_mode == 2 ? cudaEventBlockingSync : 0) | cudaEventDisableTiming));
         const size_t n = max_points;
         CK(dalloc(&h->d_in, n));
         CK(dalloc(&h->d_pts, n));
