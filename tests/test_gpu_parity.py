@@ -181,6 +181,43 @@ def test_batch_matches_single_frames(trk, oracle, synth):
         assert np.array_equal(idx[off[k0]:off[k1]], i1)
 
 
+def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
+    # several handles (one host thread + streams each) share the GPU, as in bench.py and in a multi-LiDAR deployment:
+    # every handle must produce exactly what it produces alone
+    import threading
+    p = synth.C3_PARAMS
+    sc = synth.scene_c3()
+    n_handles, rounds = 4, 6
+    frames = [sc.frame(10 + f, n_points=60000 + 5000 * f) for f in range(n_handles)]
+    refs = []
+    for fr in frames:
+        lab = oracle.labels_grid(fr, p["cluster_tolerance"])
+        refs.append(oracle.csr_from_labels(lab, p["min_cluster_size"], p["max_cluster_size"]))
+    handles = [mot.Tracker(device=0, max_points=1 << 17, max_tracks=0) for _ in range(n_handles)]
+    errors = []
+
+    def worker(i):
+        try:
+            t = handles[i]
+            t.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+            for r in range(rounds):
+                j = (i + r) % n_handles   # every handle sees every frame, in a different order
+                off, idx = t.extract(frames[j])
+                if not (np.array_equal(off, refs[j][0]) and np.array_equal(idx, refs[j][1])):
+                    errors.append((i, r, j))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(n_handles)]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join()
+    for t in handles:
+        t.close()
+    assert not errors, errors
+
+
 def test_u64_key_path_is_taken(trk, oracle):
     pts, tol, mn, mx, _ = kat_cases()["wide_extent_u64_keys"]
     check_extract(trk, oracle, pts, tol, mn, mx)
