@@ -683,6 +683,242 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse(const
     }
 }
 
+// ---- k_uf_sparse2: the same task, HALF a warp per coarse cell ------------------------------------------------------------
+// A LiDAR frame's typical coarse cell has ~9 own points and ~50 in its forward neighbourhood: one or two 32-point chunks,
+// so a whole warp per task spends most of its instructions on per-task bookkeeping (lookups, staging, cell search, edge
+// emission) that a wider warp does not make faster.  Here a warp takes two ADJACENT coarse cells, 16 lanes each: every
+// warp-uniform step of the bookkeeping serves two tasks at once (the two neighbour rows are one coalesced 128-byte load),
+// and the sweep runs 16-point chunks per task.  Same staging (TMA into a 128-point tile per task), same exact predicate,
+// same hooking protocol as k_uf_sparse; a task that does not fit the smaller tile goes to k_uf_dense.
+constexpr int UFP_TILE = 128;
+#ifndef UFP_BRUTE_V
+#define UFP_BRUTE_V 4096
+#endif
+constexpr int UFP_BRUTE_TESTS = UFP_BRUTE_V;
+struct __align__(16) UfpWarpSmem {
+    float4 tile[2][UFP_TILE];
+    int cstart[2][16];
+    int coff[2][16];
+    int ffirst[2][16];
+    unsigned char attach[2][UFC_NODES];
+    unsigned char elist[2][UFC_NODES + 16];  // compacted list of attached neighbour nodes (emission)
+    uint64_t bar;
+};
+
+__device__ __forceinline__ int seg16_inclusive_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o, 16);
+        if ((lane_id() & 15) >= o) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(const float4* __restrict__ spts, const int4* __restrict__ crec,
+                                                                             const int* __restrict__ nbr, int* __restrict__ d_counts, int* parent,
+                                                                             float r2, int use_tma, int* __restrict__ dense_list, int dense_cap) {
+    extern __shared__ __align__(16) unsigned char ufc_smem_raw[];
+    UfpWarpSmem& sm = reinterpret_cast<UfpWarpSmem*>(ufc_smem_raw)[warp_id()];
+    const int lane = lane_id(), hl = lane & 15, half = lane >> 4;
+    const unsigned hmask = 0xffffu << (half * 16);
+    const int n_tasks = d_counts[CNT_COARSE];
+    const int n_pairs = (n_tasks + 1) >> 1;
+    const int n_warps = gridDim.x * UFC_WARPS;
+    if (lane == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t parity = 0;
+    float4* const tile = sm.tile[half];
+    unsigned char* const attach = sm.attach[half];
+    // software pipeline of the lookup chain: neighbour rows two pairs ahead, records one pair ahead
+    const int first = blockIdx.x * UFC_WARPS + warp_id();
+    auto row = [&](int pair) { return (pair < n_pairs && 2 * pair + half < n_tasks) ? __ldg(nbr + pair * 32 + lane) : -1; };
+    int nci_1 = row(first), nci_2 = row(first + n_warps);
+    int4 rec_1 = make_int4(0, 0, 0, 0);
+    if (nci_1 >= 0) rec_1 = __ldg(crec + nci_1);
+
+    for (int pair = first; pair < n_pairs; pair += n_warps) {
+        int4 rec = rec_1;
+        rec_1 = make_int4(0, 0, 0, 0);
+        if (nci_2 >= 0) rec_1 = __ldg(crec + nci_2);
+        nci_2 = row(pair + 2 * n_warps);
+        const int ci = 2 * pair + half;
+        int incl = seg16_inclusive_scan(rec.y);
+        int ptot = __shfl_sync(kFull, incl, 15, 16);
+        int n_own = __shfl_sync(kFull, rec.y, 0, 16);
+        const int ffirst0 = __shfl_sync(kFull, rec.z, 0, 16);
+        int n_a = __popc((unsigned)__shfl_sync(kFull, rec.w, 0, 16));
+        const bool exists = ci < n_tasks;
+        const bool fits = ptot <= UFP_TILE && n_own * ptot <= UFP_BRUTE_TESTS;
+        if (exists && !fits && hl == 0) {  // dense neighbourhood: hand the task to k_uf_dense
+            const int slot = atomicAdd(&d_counts[CNT_DENSE], 1);
+            if (slot < dense_cap) dense_list[slot] = ci;
+            else atomicOr(&d_counts[CNT_FLAGS], 1);
+        }
+        if (!exists || !fits) {  // this half sits the pair out
+            rec.y = 0;
+            incl = 0;
+            ptot = 0;
+            n_own = 0;
+            n_a = 0;
+        }
+        if (!__any_sync(kFull, ptot > 0)) continue;
+        sm.cstart[half][hl] = rec.x;
+        sm.coff[half][hl] = incl - rec.y;  // entries 14, 15 hold ptot
+        sm.ffirst[half][hl] = rec.z;
+        for (int x = lane; x < 2 * UFC_NODES / 4; x += 32) reinterpret_cast<uint32_t*>(sm.attach)[x] = 0xffffffffu;
+        // ---- stage both forward neighbourhoods: one TMA bulk copy per occupied cell, one mbarrier for the pair ----
+        bool staged = false;
+        if (use_tma & 1) {
+            const int ptot_other = __shfl_xor_sync(kFull, ptot, 16);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.bar, (uint32_t)(ptot + ptot_other) * 16u);
+            __syncwarp();
+            if (rec.y > 0) tma_load_1d(&tile[incl - rec.y], spts + rec.x, (uint32_t)rec.y * 16u, &sm.bar);
+            const bool ok = mbar_wait_bounded(&sm.bar, parity);
+            parity ^= 1u;
+            staged = __all_sync(kFull, ok);
+        }
+        __syncwarp();
+        if (!staged) {
+            for (int t = hl; t < ptot; t += 16) {
+                int c = 0;
+#pragma unroll
+                for (int k = 8; k > 0; k >>= 1)
+                    if (c + k < UFC_CELLS && sm.coff[half][c + k] <= t) c += k;
+                tile[t] = __ldg(spts + sm.cstart[half][c] + (t - sm.coff[half][c]));
+            }
+            __syncwarp();
+        }
+
+        // ---- sweep: 16-point chunks per task while A's children are not yet one component, then 32-point chunks ----
+        unsigned long long comp = 0x8040201008040201ull;  // byte a = mask of A's children connected to child a (uniform per half)
+        int t0 = n_a == 1 ? (n_own & ~15) : 0;
+        const unsigned all_children = (1u << n_a) - 1u;
+        for (;;) {
+            const bool work = t0 < ptot;
+            if (!__any_sync(kFull, work)) break;
+            if (work && (unsigned)(comp & 0xffull) != all_children) {
+                // general chunk (see k_uf_sparse); every collective below is confined to this half
+                const int t = t0 + hl;
+                const bool valid = t < ptot;
+                int c = 0, fid = -1 - lane;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+#pragma unroll
+                    for (int k = 8; k > 0; k >>= 1)
+                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= t) c += k;
+                    q = tile[t];
+                    fid = __float_as_int(q.w);
+                }
+                unsigned hit = 0;
+#pragma unroll 4
+                for (int i = 0; i < n_own; ++i) {
+                    const float4 pi = tile[i];
+                    const unsigned bit = 1u << (unsigned)(__float_as_int(pi.w) - ffirst0);
+                    if (dist2_exact(pi.x, pi.y, pi.z, q.x, q.y, q.z) < r2) hit |= bit;
+                }
+                if (!valid) hit = 0;
+                const int j = fid - sm.ffirst[half][c];
+                if (valid && c == 0) hit &= (1u << j) - 1u;
+                const unsigned peers = __match_any_sync(hmask, fid);
+                unsigned hm = 0;
+                for (int a = 0; a < n_a; ++a) {
+                    const unsigned bal = __ballot_sync(hmask, (hit >> a) & 1u);
+                    if (bal & peers) hm |= 1u << a;
+                }
+                const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
+                if (!leader) hm = 0;
+                if (leader) {
+                    if (c == 0) hm |= 1u << j;
+                    else {
+                        const unsigned prev = attach[c * 8 + j];
+                        if (prev != 0xffu) hm |= 1u << prev;
+                        attach[c * 8 + j] = (unsigned char)(__ffs(hm) - 1);
+                    }
+                }
+                for (;;) {
+                    const unsigned lowc = hm ? (unsigned)((comp >> (8 * (__ffs(hm) - 1))) & 0xffull) : 0u;
+                    const unsigned bm = __ballot_sync(hmask, (hm & ~lowc) != 0u);
+                    if (!bm) break;
+                    const unsigned m = __shfl_sync(hmask, hm, __ffs(bm) - 1);
+                    unsigned nc = 0;
+                    for (unsigned mm = m; mm; mm &= mm - 1) nc |= (unsigned)((comp >> (8 * (__ffs(mm) - 1))) & 0xffull);
+                    for (unsigned mm = nc; mm; mm &= mm - 1) {
+                        const int sh = 8 * (__ffs(mm) - 1);
+                        comp = (comp & ~(0xffull << sh)) | ((unsigned long long)nc << sh);
+                    }
+                }
+                t0 += 16;
+            } else if (work) {
+                // fast chunk: children are one component, a lane only needs to know WHETHER its point touches A
+                const int ta = t0 + hl, tb = t0 + 16 + hl;
+                const float4 qa = ta < ptot ? tile[ta] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+                const float4 qb = tb < ptot ? tile[tb] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+                float da = 3.0e38f, db = 3.0e38f;
+#pragma unroll 4
+                for (int i = 0; i < n_own; ++i) {
+                    const float4 pi = tile[i];
+                    da = fminf(da, dist2_exact(pi.x, pi.y, pi.z, qa.x, qa.y, qa.z));
+                    db = fminf(db, dist2_exact(pi.x, pi.y, pi.z, qb.x, qb.y, qb.z));
+                }
+                if (da < r2 && ta >= n_own) {
+                    int c = 0;
+#pragma unroll
+                    for (int k = 8; k > 0; k >>= 1)
+                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= ta) c += k;
+                    attach[c * 8 + (__float_as_int(qa.w) - sm.ffirst[half][c])] = 0;
+                }
+                if (db < r2 && tb >= n_own) {
+                    int c = 0;
+#pragma unroll
+                    for (int k = 8; k > 0; k >>= 1)
+                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= tb) c += k;
+                    attach[c * 8 + (__float_as_int(qb.w) - sm.ffirst[half][c])] = 0;
+                }
+                t0 += 32;
+            }
+        }
+        __syncwarp();
+        // ---- edges: compact the attached neighbour nodes of each task (plus the links among its own children, coded as
+        // nodes 0..7 of cell 0) into a short list, then hook 16 edges per round and task, look-ahead first ----
+        int n_list = 0;
+#pragma unroll
+        for (int r = 0; r < UFC_NODES / 16; ++r) {
+            const int x = hl + 16 * r;
+            bool on;
+            if (r == 0 && hl < 8) {  // cell 0 = A itself: node hl is child hl, linked to its component's first child
+                on = hl < n_a && (__ffs((unsigned)((comp >> (8 * hl)) & 0xffull)) - 1) != hl;
+            } else {
+                on = attach[x] != 0xffu;
+            }
+            const unsigned bal = (__ballot_sync(kFull, on) >> (half * 16)) & 0xffffu;
+            if (on) sm.elist[half][n_list + __popc(bal & ((1u << hl) - 1u))] = (unsigned char)x;
+            n_list += __popc(bal);
+        }
+        __syncwarp();
+        for (int e0 = 0; __any_sync(kFull, e0 < n_list); e0 += 16) {
+            int ea = -1, eb = -1;
+            if (e0 + hl < n_list) {
+                const int x = sm.elist[half][e0 + hl];
+                const int a = x < 8 ? x : attach[x];  // own child, or the child the neighbour node touches
+                ea = sm.ffirst[half][x >> 3] + (x & 7);
+                eb = ffirst0 + __ffs((unsigned)((comp >> (8 * a)) & 0xffull)) - 1;
+            }
+            // look-ahead through L1 (stale parents are still set members), then hook the ancestors directly
+            if (ea >= 0) { ea = __ldca(parent + ea); eb = __ldca(parent + eb); }
+            if (ea >= 0) { ea = __ldca(parent + ea); eb = __ldca(parent + eb); }
+            if (ea >= 0 && ea != eb) {
+                const int hi = max(ea, eb), lo = min(ea, eb);
+                const int old = atomicMin(parent + hi, lo);
+                if (old != hi && old != lo) uf_unite(parent, old, lo);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Dense tasks (listed by k_uf_sparse).  RING 1: fine-cell pairs at Chebyshev distance <= 1; RING 2 (second launch,
 // after a global compress): distance 2.  A pair whose cells already share a global root is skipped without touching
 // a point -- on a densely sampled surface a ring-2 pair is always connected through the ring-1 cell between them --

@@ -96,6 +96,7 @@ struct mot_handle {
     // the other handles are placed on the SMs first instead of queueing behind a union-find launch (MOT_UF_PRIO=0: off).
     cudaStream_t uf_stream = nullptr;
     cudaEvent_t ev_uf[2] = {nullptr, nullptr};
+    int uf_pair = 1;           // k_uf_sparse2 (half a warp per coarse cell); MOT_UF_PAIR=0: k_uf_sparse (a warp per cell)
     int uf_blocks_per_sm = 5;  // resident CTAs of k_uf_sparse per SM (MOT_UF_BLOCKS; fewer leaves room for other streams' kernels)
     int* d_bbox = nullptr;    // 8 ints
     uint64_t* d_ckeys[2] = {nullptr, nullptr};
@@ -300,8 +301,13 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             CK(cudaStreamWaitEvent(h->uf_stream, h->ev_uf[0], 0));
             st = h->uf_stream;
         }
-        LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
-                                                                           h->uf_tma, h->d_dense_list, h->dense_cap));
+        if (h->uf_pair)
+            LAUNCH(KID_UF_COARSE, k_uf_sparse2<<<cgrid, UFC_THREADS, UFC_WARPS * sizeof(UfpWarpSmem), st>>>(h->d_spts, h->d_crec, h->d_nbr, h->d_counts,
+                                                                                                      h->d_parent, r2, h->uf_tma, h->d_dense_list,
+                                                                                                      h->dense_cap));
+        else
+            LAUNCH(KID_UF_COARSE, k_uf_sparse<<<cgrid, UFC_THREADS, usm, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
+                                                                               h->uf_tma, h->d_dense_list, h->dense_cap));
         int dgrid = cgrid < h->num_sms * 8 ? cgrid : h->num_sms * 8;
         LAUNCH(KID_UF_DENSE1, k_uf_dense<1><<<dgrid, UFC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_crec, h->d_nbr, h->d_counts, h->d_parent, r2,
                                                                             h->d_dense_list, h->dense_cap));
@@ -648,7 +654,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         for (auto& e : h->timer_ev) CK(cudaEventCreate(&e));
         h->prof.st = h->stream;
         CK(cudaFuncSetAttribute(k_uf_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(UFC_WARPS * sizeof(UfcWarpSmem))));
+        CK(cudaFuncSetAttribute(k_uf_sparse2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(UFC_WARPS * sizeof(UfpWarpSmem))));
         if (const char* e = getenv("MOT_UF_MODE")) h->uf_mode = atoi(e);
+        if (const char* e = getenv("MOT_UF_PAIR")) h->uf_pair = atoi(e);
         if (const char* e = getenv("MOT_UF_TMA")) h->uf_tma = atoi(e) & 1;  // 0: plain loads instead of TMA staging (A/B)
         CK(rs_configure<uint32_t>());
         CK(rs_configure<uint64_t>());
