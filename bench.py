@@ -106,6 +106,7 @@ def kernel_bytes(name, M, cf, cc, K, total, key_bytes, n_sort_passes, R_G=1024 *
         "k_cells_write": (kb + 4 + 16 + 16) * M + 24 * cf + 16 * cc,  # key, index, gather point, write sorted SoA point, tables
         "k_coarse_records": 12 * cf + 80 * cc,            # record (16 B) + neighbour row (64 B) per coarse cell
         "k_uf_sparse": 16 * M + 80 * cc + 8 * cf,         # every sorted point once + record/neighbour row + parent r/w
+        "k_uf_sparse2": 16 * M + 80 * cc + 8 * cf,        # same traffic, half a warp per coarse cell
         "k_uf_flatten<in-place>": 8 * cf,
         "k_uf_flatten<root>": 8 * cf,
         "k_comp_accumulate": 16 * cf,
@@ -353,7 +354,7 @@ def run_b200(args, rank, world, local_rank):
 
     # north_star's sub-target: grid build + union-find against (104 + 16 P) M + 16 C bytes
     k15 = ("k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count", "k_hash_clear", "k_cells_write",
-           "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_uf_flatten<in-place>", "k_uf_flatten<root>",
+           "k_coarse_records", "k_uf_sparse", "k_uf_sparse2", "k_uf_dense<1>", "k_uf_dense<2>", "k_uf_flatten<in-place>", "k_uf_flatten<root>",
            "k_uf_pairs<1>", "k_uf_pairs<2>")
     t15_us = sum(v[0] for kname, v in prof.items() if kname in k15) / prof_steps * 1e3
     b15 = (104 + 16 * P) * M + 16 * grid["coarse_cells"]

@@ -50,7 +50,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -58,7 +58,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2"};
 
 struct mot_handle {
     int device = 0;
@@ -302,7 +302,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             st = h->uf_stream;
         }
         if (h->uf_pair)
-            LAUNCH(KID_UF_COARSE, k_uf_sparse2<<<cgrid, UFC_THREADS, UFC_WARPS * sizeof(UfpWarpSmem), st>>>(h->d_spts, h->d_crec, h->d_nbr, h->d_counts,
+            LAUNCH(KID_UF_PAIR, k_uf_sparse2<<<cgrid, UFC_THREADS, UFC_WARPS * sizeof(UfpWarpSmem), st>>>(h->d_spts, h->d_crec, h->d_nbr, h->d_counts,
                                                                                                       h->d_parent, r2, h->uf_tma, h->d_dense_list,
                                                                                                       h->dense_cap));
         else
