@@ -702,6 +702,7 @@ struct __align__(16) UfpWarpSmem {
     int ffirst[2][16];
     unsigned char attach[2][UFC_NODES];
     unsigned char elist[2][UFC_NODES + 16];  // compacted list of attached neighbour nodes (emission)
+    unsigned char cellof[2][UFP_TILE];       // stencil cell (0..13) of every tile position, written once per task
     uint64_t bar;
 };
 
@@ -769,6 +770,7 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(cons
         sm.coff[half][hl] = incl - rec.y;  // entries 14, 15 hold ptot
         sm.ffirst[half][hl] = rec.z;
         for (int x = lane; x < 2 * UFC_NODES / 4; x += 32) reinterpret_cast<uint32_t*>(sm.attach)[x] = 0xffffffffu;
+        for (int k = 0; k < rec.y; ++k) sm.cellof[half][incl - rec.y + k] = (unsigned char)hl;  // lane hl owns stencil cell hl
         // ---- stage both forward neighbourhoods: one TMA bulk copy per occupied cell, one mbarrier for the pair ----
         bool staged = false;
         if (use_tma & 1) {
@@ -806,9 +808,7 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(cons
                 int c = 0, fid = -1 - lane;
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) {
-#pragma unroll
-                    for (int k = 8; k > 0; k >>= 1)
-                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= t) c += k;
+                    c = sm.cellof[half][t];
                     q = tile[t];
                     fid = __float_as_int(q.w);
                 }
@@ -823,11 +823,7 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(cons
                 const int j = fid - sm.ffirst[half][c];
                 if (valid && c == 0) hit &= (1u << j) - 1u;
                 const unsigned peers = __match_any_sync(hmask, fid);
-                unsigned hm = 0;
-                for (int a = 0; a < n_a; ++a) {
-                    const unsigned bal = __ballot_sync(hmask, (hit >> a) & 1u);
-                    if (bal & peers) hm |= 1u << a;
-                }
+                unsigned hm = __reduce_or_sync(peers, hit);  // children of A touched by any point of this fine cell
                 const bool leader = valid && lane == __ffs(peers) - 1 && hm != 0;
                 if (!leader) hm = 0;
                 if (leader) {
@@ -864,17 +860,11 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(cons
                     db = fminf(db, dist2_exact(pi.x, pi.y, pi.z, qb.x, qb.y, qb.z));
                 }
                 if (da < r2 && ta >= n_own) {
-                    int c = 0;
-#pragma unroll
-                    for (int k = 8; k > 0; k >>= 1)
-                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= ta) c += k;
+                    const int c = sm.cellof[half][ta];
                     attach[c * 8 + (__float_as_int(qa.w) - sm.ffirst[half][c])] = 0;
                 }
                 if (db < r2 && tb >= n_own) {
-                    int c = 0;
-#pragma unroll
-                    for (int k = 8; k > 0; k >>= 1)
-                        if (c + k < UFC_CELLS && sm.coff[half][c + k] <= tb) c += k;
+                    const int c = sm.cellof[half][tb];
                     attach[c * 8 + (__float_as_int(qb.w) - sm.ffirst[half][c])] = 0;
                 }
                 t0 += 32;
