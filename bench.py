@@ -397,14 +397,16 @@ def wedge(frame, frac):
 
 def cpu_baseline(frame, p):
     """The oracle's restatement of the reference path (KD-tree built twice + BFS, 1 thread -- the reference is single
-    threaded, MOT.cpp:117-121) on half of one frame of the step (bounded: ~15-25 s of CPU work)."""
+    threaded, MOT.cpp:117-121) on a 162-degree azimuth wedge of one frame of the step (bounded: ~15-20 s of CPU work; the
+    cost is far from linear in the wedge -- the densely sampled near-range surfaces dominate it -- so the figure is
+    quoted together with the sample it was taken on)."""
     oracle = entry.load_oracle()
-    w = wedge(frame, 0.5)  # half of the frame's azimuth range at full density: ~15-25 s of single-thread CPU work
+    w = wedge(frame, 0.45)
     t0 = time.perf_counter()
     off, idx = oracle.cluster_kdtree(w, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], build_twice=True)
     dt = time.perf_counter() - t0
     return {"value": round(len(w) / dt / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"180-degree azimuth wedge of frame 0 ({len(w)} points, {len(off) - 1} clusters), {dt:.1f} s, oracle KD-tree+BFS restatement of PCL"}
+            "sample": f"162-degree azimuth wedge of frame 0 ({len(w)} points, {len(off) - 1} clusters), {dt:.1f} s, oracle KD-tree+BFS restatement of PCL"}
 
 
 def run_reference(args, rank, world):
