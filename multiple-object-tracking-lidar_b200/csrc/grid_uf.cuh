@@ -957,18 +957,24 @@ __global__ void __launch_bounds__(UFC_THREADS) k_uf_dense(const float4* __restri
                     elig = (RING == 1 ? ring <= 1 : ring == 2) && uf_find(parent, s_ffirst[w][c] + j) != uf_find(parent, fid_a);
                 }
                 unsigned bm = __ballot_sync(kFull, elig);
+                bool dirty = false;  // this warp has hooked something since the roots above were compared
                 while (bm) {
                     const int sl = __ffs(bm) - 1;
                     bm &= bm - 1;
                     const int nd = nb0 + sl;
                     const int fid_b = s_ffirst[w][nd >> 3] + (nd & 7);
-                    int same = 0;
-                    if (lane == 0) same = uf_find(parent, fid_b) == uf_find(parent, fid_a);
-                    same = __shfl_sync(kFull, same, 0);
-                    if (same) continue;
+                    if (dirty) {  // an earlier hook of this chunk may have joined the two cells already
+                        int same = 0;
+                        if (lane == 0) same = uf_find(parent, fid_b) == uf_find(parent, fid_a);
+                        same = __shfl_sync(kFull, same, 0);
+                        if (same) continue;
+                    }
                     const int b0 = __ldg(fc_start + fid_b), b1 = __ldg(fc_start + fid_b + 1);
                     const bool found = coop_witness(spts, a0, a1, b0, b1, r2);
-                    if (found && lane == 0) uf_unite(parent, fid_a, fid_b);
+                    if (found) {
+                        if (lane == 0) uf_unite(parent, fid_a, fid_b);
+                        dirty = true;
+                    }
                     __syncwarp();
                 }
             }
