@@ -218,6 +218,46 @@ def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
     assert not errors, errors
 
 
+ALTERNATIVES = [{"MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"},
+                {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}, {"MOT_UF_BLOCKS": "3"}]
+
+
+@pytest.mark.parametrize("env", ALTERNATIVES, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_alternative_paths_keep_parity(mot, oracle, synth, env):
+    # every A/B switch (README) selects a different kernel or host path for the same result: known answers, one LiDAR
+    # frame slice with dense and sparse neighbourhoods, one frame batch
+    saved = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        t = mot.Tracker(device=0, max_points=1 << 19, max_tracks=0)   # the switches are read by mot_create
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for name in ("bridged_blobs", "pair_exactly_tol", "pair_tol_minus_ulp", "duplicates", "uniform_dense", "size_filter_edges", "empty"):
+        if name in kat_cases():
+            pts, tol, mn, mx, _ = kat_cases()[name]
+            check_extract(t, oracle, pts, tol, mn, mx)
+    p = synth.C2_PARAMS
+    frame = synth.scene_c2().frame(3)
+    az = np.arctan2(frame[:, 1], frame[:, 0])
+    wedge = np.ascontiguousarray(frame[np.abs(az) < 0.6])
+    check_extract(t, oracle, wedge, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], brute=False)
+    p3 = synth.C3_PARAMS
+    sc3 = synth.scene_c3()
+    frames = [sc3.frame(40 + f, n_points=30000) for f in range(3)]
+    t.set_cluster_params(p3["cluster_tolerance"], p3["min_cluster_size"], p3["max_cluster_size"])
+    fco, off, idx = t.extract_batch(frames)
+    for f, fr in enumerate(frames):
+        lab = oracle.labels_grid(fr, p3["cluster_tolerance"])
+        o_ref, i_ref = oracle.csr_from_labels(lab, p3["min_cluster_size"], p3["max_cluster_size"])
+        k0, k1 = fco[f], fco[f + 1]
+        assert np.array_equal(off[k0:k1 + 1] - off[k0], o_ref) and np.array_equal(idx[off[k0]:off[k1]], i_ref)
+    t.close()
+
+
 def test_u64_key_path_is_taken(trk, oracle):
     pts, tol, mn, mx, _ = kat_cases()["wide_extent_u64_keys"]
     check_extract(trk, oracle, pts, tol, mn, mx)
