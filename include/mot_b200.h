@@ -144,6 +144,10 @@ int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remov
 int mot_result_counts(mot_handle* h, size_t* m, int32_t* n_clusters, size_t* n_indices);
 /* Grid statistics of the last result: occupied fine (clique) cells, occupied coarse cells, voxel key width. */
 int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, int32_t* key_bits);
+/* Internal device counters of the last result (diagnostics for the benches and tests, no reference counterpart): [0] fine
+ * cells, [1] coarse cells, [2] clusters, [3] indices, [4] flags, [5] kept points, [9]/[10] fine-cell pairs handed to the
+ * cooperative witness search (ring 1 / ring 2), [12] pairs searched serially because that list was full; up to 16 ints. */
+int mot_result_counters(mot_handle* h, int32_t* out, int capacity);
 /* Device pointers of the last result (valid until the next call on the handle). */
 int mot_result_device_ptrs(mot_handle* h, const float** d_kept_xyz16, const int32_t** d_cluster_offsets,
                            const int32_t** d_point_indices, const mot_cluster_stat** d_stats,

@@ -98,6 +98,7 @@ SYMBOLS = {
     "mot_frame_device": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_int, C.c_int, C.c_double]),
     "mot_result_counts": (C.c_int, [_H, C.POINTER(_SIZE), C.POINTER(C.c_int32), C.POINTER(_SIZE)]),
     "mot_result_grid": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mot_result_counters": (C.c_int, [_H, _i32, C.c_int]),
     "mot_result_device_ptrs": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 5),
     "mot_result_fetch": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, C.c_void_p, _SIZE]),
     "mot_result_labels": (C.c_int, [_H, C.c_void_p, _SIZE]),
@@ -265,6 +266,11 @@ class Tracker:
         a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
         self._ck(self.lib.mot_result_grid(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(fine_cells=a.value, coarse_cells=b.value, key_bits=c.value)
+
+    def result_counters(self):
+        out = np.zeros(16, dtype=np.int32)
+        self._ck(self.lib.mot_result_counters(self.h, out, 16))
+        return out
 
     def result_device_ptrs(self):
         ps = [C.c_void_p() for _ in range(5)]

@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
                                                                int* __restrict__ cc_first,
                                                                int* __restrict__ parent, int* __restrict__ csize, int* __restrict__ cmin,
                                                                int* __restrict__ crank, KT* __restrict__ hkeys, int* __restrict__ hvals,
-                                                               unsigned hmask, int hshift, int* __restrict__ d_counts) {
+                                                               unsigned hmask, int hshift, int* __restrict__ d_counts,
+                                                               KT* __restrict__ ckey_out /* sorted coarse keys (cell_uf.cuh), may be null */) {
     __shared__ int scratch[36];
     {
         const int hb = d_counts[CNT_HB];  // set by k_hash_clear
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
             if (ch) {
                 const int ci = cbase + (excl >> 16);
                 cc_first[ci] = fi;
+                if (ckey_out) ckey_out[ci] = k >> 3;
                 hash_insert<KT>(hkeys, hvals, hmask, hshift, k >> 3, ci);
             }
         }

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/mot_b200.h"
+#include "cell_uf.cuh"
 #include "cluster_table.cuh"
 #include "common.cuh"
 #include "grid_uf.cuh"
@@ -50,7 +51,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -58,7 +59,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>"};
 
 struct mot_handle {
     int device = 0;
@@ -111,7 +112,15 @@ struct mot_handle {
     int* d_dense_list = nullptr;
     int* d_nbr = nullptr;
     int dense_cap = 0;
-    int uf_mode = 1;   // 1: coarse-cell warps + TMA staging + local union-find (default); 0: v1 two-phase fine-cell warps
+    int uf_mode = 2;   // 2: cell boxes + local components + thread per (cell, neighbour row) (cell_uf.cuh, default);
+                       // 1: coarse-cell warps + TMA staging + brute-force sweep; 0: v1 two-phase fine-cell warps
+    void* d_ckey = nullptr;      // sorted coarse keys (u32 or u64)
+    float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
+    int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
+    int heavy_cap = 0;
+    int uf_light = 64;      // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
+    int uf_cross_blocks = 8;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
+    int uf_split = 0;        // MOT_UF_SPLIT=1: face rows and the remaining rows as two launches
     int uf_tma = 1;
     float4* d_centroids = nullptr;
     PairCand* d_cands = nullptr;
@@ -147,6 +156,7 @@ struct mot_handle {
     const float4* res_cloud = nullptr;  // the clustered cloud on the device (d_pts or the caller's pointer)
     int res_M = 0, res_K = 0, res_total = 0, res_idx_buf = 0, res_frames = 1;
     int res_fine = 0, res_coarse = 0, res_key_bits = 0;
+    int res_counters[CNT_N] = {};
     int sorted_buf = 0;
     bool res_centroids = false;
     Prof prof;
@@ -277,7 +287,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                               h->d_counts));
+                                                                               h->d_counts, h->uf_mode == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr));
     CK(cudaEventRecord(h->ev[2], st));
 
     const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
@@ -285,7 +295,39 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (uf_grid > h->num_sms * 8) uf_grid = h->num_sms * 8;
     int flat_grid = (M + 255) / 256;
     if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
-    if (h->uf_mode == 1) {
+    if (h->uf_mode == 2) {
+        const cudaStream_t main_st = st;
+        const bool side = h->uf_stream && !h->prof.on;
+        if (side) {
+            CK(cudaEventRecord(h->ev_uf[0], main_st));
+            CK(cudaStreamWaitEvent(h->uf_stream, h->ev_uf[0], 0));
+            st = h->uf_stream;
+        }
+        int lgrid = (M + CLOC_THREADS - 1) / CLOC_THREADS;
+        if (lgrid > h->num_sms * 16) lgrid = h->num_sms * 16;
+        LAUNCH(KID_CELL_LOCAL, k_cell_local<KT><<<lgrid, CLOC_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, h->d_counts, r2, h->uf_light,
+                                                                               h->d_crec, h->d_cbox, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
+                                                                               h->heavy_cap));
+        int xgrid = (M + UFX_THREADS - 1) / UFX_THREADS;
+        if (xgrid > h->num_sms * h->uf_cross_blocks) xgrid = h->num_sms * h->uf_cross_blocks;
+        const int n_split = h->uf_split ? 2 : 1;
+        for (int part = 0; part < n_split; ++part) {
+            const int rb = n_split == 1 ? 0 : (part == 0 ? 0 : 3), re = n_split == 1 ? 5 : (part == 0 ? 3 : 5);
+            LAUNCH(KID_UF_CROSS, k_uf_cross<KT><<<xgrid, UFX_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec, h->d_cbox, h->d_fbox,
+                                                                              h->d_spts, reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts,
+                                                                              h->d_parent, g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, rb, re));
+        }
+        const int hgrid = h->num_sms * 8;
+        LAUNCH(KID_UF_HEAVY1, k_uf_heavy<<<hgrid, UFH_THREADS, 0, st>>>(h->d_spts, h->d_fbox, h->d_heavy1, h->d_counts + CNT_HEAVY1, h->heavy_cap, h->d_parent, r2));
+        LAUNCH(KID_FLATTEN_IF, k_uf_flatten_if<<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_counts, h->d_counts + CNT_HEAVY2));
+        LAUNCH(KID_UF_HEAVY2, k_uf_heavy<<<hgrid, UFH_THREADS, 0, st>>>(h->d_spts, h->d_fbox, h->d_heavy2, h->d_counts + CNT_HEAVY2, h->heavy_cap, h->d_parent, r2));
+        LAUNCH(KID_FLATTEN2, k_uf_flatten<false><<<flat_grid, 256, 0, st>>>(h->d_parent, h->d_root, h->d_counts));
+        if (side) {
+            CK(cudaEventRecord(h->ev_uf[1], st));
+            st = main_st;
+            CK(cudaStreamWaitEvent(st, h->ev_uf[1], 0));
+        }
+    } else if (h->uf_mode == 1) {
         int rgrid = (M + 15) / 16;
         if (rgrid > h->num_sms * 32) rgrid = h->num_sms * 32;
         LAUNCH(KID_COARSE_REC, k_coarse_records<KT><<<rgrid, 256, 0, st>>>(skeys, h->d_fc_start, h->d_cc_first, h->d_counts,
@@ -413,6 +455,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     const int total = h->h_pinned[8 + CNT_TOTAL];
     h->res_K = K;
     h->res_total = total;
+    std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
     if (h->h_pinned[8 + CNT_FLAGS] & 2) return fail(h, MOT_ERR_CUDA, "radix sort look-back exceeded its spin limit");
     h->res_fine = h->h_pinned[8 + CNT_FINE];
@@ -628,6 +671,15 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->dense_cap = (int)(n / 4 + 1024);  // a dense task's forward neighbourhood holds >= 64 points and a point lies in <= 14 of them
         CK(dalloc(&h->d_dense_list, (size_t)h->dense_cap));
         CK(dalloc(&h->d_nbr, n * 16));
+        CK(cudaMalloc(&h->d_ckey, (n + 1) * 8 + 256));
+        CK(dalloc(&h->d_cbox, 2 * n));
+        CK(dalloc(&h->d_fbox, 2 * n));
+        h->heavy_cap = (int)(n / 2 + 4096);
+        CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
+        CK(dalloc(&h->d_heavy2, (size_t)h->heavy_cap));
+        if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
+        if (const char* e = getenv("MOT_UF_XBLOCKS")) h->uf_cross_blocks = std::min(32, std::max(1, atoi(e)));
+        if (const char* e = getenv("MOT_UF_SPLIT")) h->uf_split = atoi(e) != 0;
         int hb = ceil_log2(2 * (long long)n);
         if (hb < 4) hb = 4;
         h->hash_capacity = (size_t)1 << hb;
@@ -702,7 +754,7 @@ int mot_destroy(mot_handle* h) {
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
                     h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
-                    h->d_ent_occ, h->d_centroids_in};
+                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1010,6 +1062,13 @@ int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, i
     if (fine_cells) *fine_cells = h->res_fine;
     if (coarse_cells) *coarse_cells = h->res_coarse;
     if (key_bits) *key_bits = h->res_key_bits;
+    return MOT_OK;
+}
+
+int mot_result_counters(mot_handle* h, int32_t* out, int capacity) {
+    if (!h || !out || capacity < 1) return MOT_ERR_INVALID;
+    if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
+    for (int i = 0; i < capacity; ++i) out[i] = i < CNT_N ? h->res_counters[i] : 0;
     return MOT_OK;
 }
 

@@ -218,8 +218,9 @@ def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
     assert not errors, errors
 
 
-ALTERNATIVES = [{"MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"},
-                {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}, {"MOT_UF_BLOCKS": "3"}]
+ALTERNATIVES = [{"MOT_UF_MODE": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_LIGHT": "1"}, {"MOT_UF_LIGHT": "1024"},
+                {"MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"},
+                {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}]
 
 
 @pytest.mark.parametrize("env", ALTERNATIVES, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
