@@ -148,6 +148,9 @@ int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, i
  * cells, [1] coarse cells, [2] clusters, [3] indices, [4] flags, [5] kept points, [9]/[10] fine-cell pairs handed to the
  * cooperative witness search (ring 1 / ring 2), [12] pairs searched serially because that list was full; up to 16 ints. */
 int mot_result_counters(mot_handle* h, int32_t* out, int capacity);
+/* Union-find diagnostics accumulated since the last call (finds, parent hops, unions, ...; cell_uf.cuh ST_*).  Only a
+ * library built with -DMOT_UF_STATS counts (returns 1); the product build returns 0 and zeroes. */
+int mot_debug_stats(mot_handle* h, uint64_t* out, int capacity);
 /* Device pointers of the last result (valid until the next call on the handle). */
 int mot_result_device_ptrs(mot_handle* h, const float** d_kept_xyz16, const int32_t** d_cluster_offsets,
                            const int32_t** d_point_indices, const mot_cluster_stat** d_stats,

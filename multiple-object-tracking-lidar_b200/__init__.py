@@ -99,6 +99,7 @@ SYMBOLS = {
     "mot_result_counts": (C.c_int, [_H, C.POINTER(_SIZE), C.POINTER(C.c_int32), C.POINTER(_SIZE)]),
     "mot_result_grid": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mot_result_counters": (C.c_int, [_H, _i32, C.c_int]),
+    "mot_debug_stats": (C.c_int, [_H, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_int]),
     "mot_result_device_ptrs": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 5),
     "mot_result_fetch": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, C.c_void_p, _SIZE]),
     "mot_result_labels": (C.c_int, [_H, C.c_void_p, _SIZE]),
@@ -271,6 +272,16 @@ class Tracker:
         out = np.zeros(16, dtype=np.int32)
         self._ck(self.lib.mot_result_counters(self.h, out, 16))
         return out
+
+    def debug_stats(self):
+        """Union-find counters of a -DMOT_UF_STATS build (None for the product build)."""
+        out = np.zeros(16, dtype=np.uint64)
+        rc = self.lib.mot_debug_stats(self.h, out, 16)
+        if rc < 0:
+            self._ck(rc)
+        names = ("finds", "hops", "unites", "cas_retry", "fine_pairs", "witness_tests", "cross_pairs", "root_skips", "cbox_rejects", "accepts",
+                 "rejects", "local_pairs", "max_hops")
+        return dict(zip(names, (int(v) for v in out))) if rc == 1 else None
 
     def result_device_ptrs(self):
         ps = [C.c_void_p() for _ in range(5)]

@@ -26,7 +26,7 @@
 namespace mot {
 
 // d_counts layout (ints)
-enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_HB = 8, CNT_N = 16 };
+enum { CNT_FINE = 0, CNT_COARSE = 1, CNT_K = 2, CNT_TOTAL = 3, CNT_FLAGS = 4, CNT_M = 5, CNT_DENSE = 6, CNT_HB = 8, CNT_N = 24 };
 
 struct GridCodec {
     double minx, miny, minz, inv_e;
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
                                                                int* __restrict__ parent, int* __restrict__ csize, int* __restrict__ cmin,
                                                                int* __restrict__ crank, KT* __restrict__ hkeys, int* __restrict__ hvals,
                                                                unsigned hmask, int hshift, int* __restrict__ d_counts,
-                                                               KT* __restrict__ ckey_out /* sorted coarse keys (cell_uf.cuh), may be null */) {
+                                                               KT* __restrict__ ckey_out /* sorted coarse keys (cell_uf.cuh), may be null */,
+                                                               unsigned char* __restrict__ fcode_out /* child code of every fine cell, may be null */) {
     __shared__ int scratch[36];
     {
         const int hb = d_counts[CNT_HB];  // set by k_hash_clear
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
                 csize[fi] = 0;
                 cmin[fi] = (int)svals[j];  // stable sort: the first point of a cell has its smallest original index
                 crank[fi] = -1;
+                if (fcode_out) fcode_out[fi] = (unsigned char)(k & 7);
             }
             if (ch) {
                 const int ci = cbase + (excl >> 16);

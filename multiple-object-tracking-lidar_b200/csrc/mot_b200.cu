@@ -51,7 +51,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -59,7 +59,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused"};
 
 struct mot_handle {
     int device = 0;
@@ -115,12 +115,20 @@ struct mot_handle {
     int uf_mode = 2;   // 2: cell boxes + local components + thread per (cell, neighbour row) (cell_uf.cuh, default);
                        // 1: coarse-cell warps + TMA staging + brute-force sweep; 0: v1 two-phase fine-cell warps
     void* d_ckey = nullptr;      // sorted coarse keys (u32 or u64)
+    unsigned char* d_fcode = nullptr;  // child code (0..7) of every fine cell
     float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
     int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
     int heavy_cap = 0;
     int uf_light = 64;      // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
-    int uf_cross_blocks = 8;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
+    int uf_cross_blocks = 4;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
     int uf_split = 0;        // MOT_UF_SPLIT=1: face rows and the remaining rows as two launches
+    int uf_xmode = 2;        // MOT_UF_XMODE 2: k_uf_fused (default); 1: k_uf_survivors + k_uf_walk per phase; 0: k_uf_cross
+    unsigned uf_phases[3] = {0x01u, 0x06u, 0x18u};  // neighbour rows per phase (MOT_UF_PHASES, e.g. "1,6,24")
+    int uf_n_phases = 3;
+    int2* d_tasks = nullptr;  // surviving cell pairs of one phase (A | code << 27, B)
+    int task_cap = 0;
+    int uf_walk_blocks = 8;   // resident CTAs of k_uf_walk per SM (MOT_UF_WBLOCKS)
+    int uf_fused_blocks = UFF_MIN_BLOCKS;  // resident CTAs of k_uf_fused per SM (MOT_UF_FBLOCKS)
     int uf_tma = 1;
     float4* d_centroids = nullptr;
     PairCand* d_cands = nullptr;
@@ -287,7 +295,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                               h->d_counts, h->uf_mode == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr));
+                                                                               h->d_counts, h->uf_mode == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr, h->uf_mode == 2 ? h->d_fcode : nullptr));
     CK(cudaEventRecord(h->ev[2], st));
 
     const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
@@ -304,10 +312,31 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             st = h->uf_stream;
         }
         int lgrid = (M + CLOC_THREADS - 1) / CLOC_THREADS;
-        if (lgrid > h->num_sms * 16) lgrid = h->num_sms * 16;
-        LAUNCH(KID_CELL_LOCAL, k_cell_local<KT><<<lgrid, CLOC_THREADS, 0, st>>>(skeys, h->d_spts, h->d_fc_start, h->d_cc_first, h->d_counts, r2, h->uf_light,
+        if (lgrid > h->num_sms * 7) lgrid = h->num_sms * 7;
+        LAUNCH(KID_CELL_LOCAL, k_cell_local<<<lgrid, CLOC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2, h->uf_light,
                                                                                h->d_crec, h->d_cbox, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
                                                                                h->heavy_cap));
+        if (h->uf_xmode == 2) {
+            int fgrid = (M + UFF_THREADS - 1) / UFF_THREADS;
+            if (fgrid > h->num_sms * h->uf_fused_blocks) fgrid = h->num_sms * h->uf_fused_blocks;
+            LAUNCH(KID_UF_FUSED, k_uf_fused<KT><<<fgrid, UFF_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec, h->d_fbox, h->d_spts,
+                                                                              reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts, h->d_parent,
+                                                                              g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap));
+        } else if (h->uf_xmode == 1) {
+            int sgrid = (M + UFS_THREADS - 1) / UFS_THREADS;
+            if (sgrid > h->num_sms * 8) sgrid = h->num_sms * 8;
+            int wgrid = (M + UFW_THREADS - 1) / UFW_THREADS;
+            if (wgrid > h->num_sms * h->uf_walk_blocks) wgrid = h->num_sms * h->uf_walk_blocks;
+            for (int ph = 0; ph < h->uf_n_phases; ++ph) {
+                LAUNCH(KID_UF_SURV, k_uf_survivors<KT><<<sgrid, UFS_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec,
+                                                                                     reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts,
+                                                                                     h->d_parent, g, h->uf_phases[ph], h->d_tasks, h->task_cap,
+                                                                                     h->d_counts + CNT_TASKS0 + ph));
+                LAUNCH(KID_UF_WALK, k_uf_walk<<<wgrid, UFW_THREADS, 0, st>>>(h->d_tasks, h->d_counts + CNT_TASKS0 + ph, h->task_cap,
+                                                                            h->d_counts + CNT_TICKET0 + ph, h->d_crec, h->d_fbox, h->d_spts, h->d_parent, r2,
+                                                                            h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, h->d_counts));
+            }
+        } else {
         int xgrid = (M + UFX_THREADS - 1) / UFX_THREADS;
         if (xgrid > h->num_sms * h->uf_cross_blocks) xgrid = h->num_sms * h->uf_cross_blocks;
         const int n_split = h->uf_split ? 2 : 1;
@@ -316,6 +345,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             LAUNCH(KID_UF_CROSS, k_uf_cross<KT><<<xgrid, UFX_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec, h->d_cbox, h->d_fbox,
                                                                               h->d_spts, reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts,
                                                                               h->d_parent, g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, rb, re));
+        }
         }
         const int hgrid = h->num_sms * 8;
         LAUNCH(KID_UF_HEAVY1, k_uf_heavy<<<hgrid, UFH_THREADS, 0, st>>>(h->d_spts, h->d_fbox, h->d_heavy1, h->d_counts + CNT_HEAVY1, h->heavy_cap, h->d_parent, r2));
@@ -457,6 +487,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_total = total;
     std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
+    if (h->h_pinned[8 + CNT_FLAGS] & 4) return fail(h, MOT_ERR_CAPACITY, "cell-pair task list overflow (internal capacity)");
     if (h->h_pinned[8 + CNT_FLAGS] & 2) return fail(h, MOT_ERR_CUDA, "radix sort look-back exceeded its spin limit");
     h->res_fine = h->h_pinned[8 + CNT_FINE];
     h->res_coarse = h->h_pinned[8 + CNT_COARSE];
@@ -619,7 +650,7 @@ extern "C" {
 const char* mot_version(void) { return "mot_b200 0.1 (sm_100a)"; }
 
 int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** out) {
-    if (!out || max_points == 0 || max_points > 0x7ffffff0ull) return MOT_ERR_INVALID;
+    if (!out || max_points == 0 || max_points > ((size_t)1 << 27)) return MOT_ERR_INVALID;  // cell indices are packed into 27 bits / int row offsets
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return MOT_ERR_CUDA;
@@ -672,6 +703,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_dense_list, (size_t)h->dense_cap));
         CK(dalloc(&h->d_nbr, n * 16));
         CK(cudaMalloc(&h->d_ckey, (n + 1) * 8 + 256));
+        CK(dalloc(&h->d_fcode, n));
         CK(dalloc(&h->d_cbox, 2 * n));
         CK(dalloc(&h->d_fbox, 2 * n));
         h->heavy_cap = (int)(n / 2 + 4096);
@@ -680,6 +712,34 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
         if (const char* e = getenv("MOT_UF_XBLOCKS")) h->uf_cross_blocks = std::min(32, std::max(1, atoi(e)));
         if (const char* e = getenv("MOT_UF_SPLIT")) h->uf_split = atoi(e) != 0;
+        if (const char* e = getenv("MOT_UF_XMODE")) h->uf_xmode = atoi(e);
+        if (const char* e = getenv("MOT_UF_PHASES")) {  // comma separated row masks; rows left out by every phase go to the last one
+            unsigned seen = 0;
+            int np = 0;
+            for (const char* c = e; *c && np < 3;) {
+                h->uf_phases[np] = (unsigned)strtoul(c, nullptr, 10) & 0x1fu & ~seen;
+                seen |= h->uf_phases[np++];
+                while (*c && *c != ',') ++c;
+                if (*c == ',') ++c;
+            }
+            if (np > 0) {
+                h->uf_phases[np - 1] |= 0x1fu & ~seen;
+                h->uf_n_phases = np;
+            }
+        }
+        if (const char* e = getenv("MOT_UF_FBLOCKS")) h->uf_fused_blocks = std::min(16, std::max(1, atoi(e)));
+        if (const char* e = getenv("MOT_UF_WBLOCKS")) h->uf_walk_blocks = std::min(16, std::max(1, atoi(e)));
+        {   // a phase lists at most (its neighbour slots) x (coarse cells <= points) tasks
+            int worst = 1;
+            for (int ph = 0; ph < h->uf_n_phases; ++ph) {
+                int slots = 0;
+                for (int row = 0; row < 5; ++row)
+                    if ((h->uf_phases[ph] >> row) & 1u) slots += row == 0 ? 1 : 3;
+                worst = std::max(worst, slots);
+            }
+            h->task_cap = (int)std::min<size_t>((size_t)worst * n + 64, 0x7ffffff0ull);
+        }
+        CK(dalloc(&h->d_tasks, (size_t)h->task_cap));
         int hb = ceil_log2(2 * (long long)n);
         if (hb < 4) hb = 4;
         h->hash_capacity = (size_t)1 << hb;
@@ -754,7 +814,7 @@ int mot_destroy(mot_handle* h) {
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
                     h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
-                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2};
+                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1070,6 +1130,23 @@ int mot_result_counters(mot_handle* h, int32_t* out, int capacity) {
     if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
     for (int i = 0; i < capacity; ++i) out[i] = i < CNT_N ? h->res_counters[i] : 0;
     return MOT_OK;
+}
+
+int mot_debug_stats(mot_handle* h, uint64_t* out, int capacity) {
+    if (!h || !out || capacity < 1) return MOT_ERR_INVALID;
+    for (int i = 0; i < capacity; ++i) out[i] = 0;
+#ifdef MOT_UF_STATS
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long tmp[ST_N];
+    CK(cudaMemcpyFromSymbol(tmp, g_uf_stats, sizeof(tmp)));
+    for (int i = 0; i < capacity && i < ST_N; ++i) out[i] = tmp[i];
+    std::memset(tmp, 0, sizeof(tmp));
+    CK(cudaMemcpyToSymbol(g_uf_stats, tmp, sizeof(tmp)));
+    return 1;
+#else
+    return MOT_OK;
+#endif
 }
 
 int mot_result_device_ptrs(mot_handle* h, const float** d_kept, const int32_t** d_offsets, const int32_t** d_indices,

@@ -16,8 +16,11 @@ namespace mot {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 pairs per tile
+#ifndef RS_ITEMS_V
+#define RS_ITEMS_V 8
+#endif
+constexpr int RS_ITEMS = RS_ITEMS_V;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // pairs per tile (2048 at 8 items per thread)
 constexpr int RS_MAX_BITS = 10;
 #ifndef RS_MAX_GRID_V
 #define RS_MAX_GRID_V 1184

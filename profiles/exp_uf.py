@@ -63,6 +63,11 @@ for var in variants:
         trk.timer_start()
         trk.cluster_batch_device(d.data_ptr(), fo)
         ts.append(trk.timer_stop())
+    trk.debug_stats()
+    trk.cluster_batch_device(d.data_ptr(), fo)
+    st = trk.debug_stats()
+    if st:
+        print("    stats of one call:", st)
     trk.set_profiling(True)
     for _ in range(reps):
         trk.cluster_batch_device(d.data_ptr(), fo)
