@@ -139,10 +139,15 @@ __device__ __forceinline__ float pt_box_lower(const float4& p, const float4& lo,
 // serial witness search between two small fine cells (points [a0, a0+na) and [b0, b0+nb)), early exit
 __device__ __forceinline__ bool light_witness(const float4* __restrict__ spts, int a0, int na, int b0, int nb, const float4& blo, const float4& bhi,
                                               float r2) {
+    {   // the first pair decides most searches: request both points at once (one round trip instead of two)
+        const float4 p = __ldg(spts + a0), q = __ldg(spts + b0);
+        UFSTAT(ST_WITNESS_TESTS, 1);
+        if (dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < r2) return true;
+    }
     for (int i = 0; i < na; ++i) {
         const float4 p = __ldg(spts + a0 + i);
         if (!(pt_box_lower(p, blo, bhi) < r2)) continue;
-        for (int j = 0; j < nb; ++j) {
+        for (int j = i == 0 ? 1 : 0; j < nb; ++j) {
             const float4 q = __ldg(spts + b0 + j);
             UFSTAT(ST_WITNESS_TESTS, 1);
             if (dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < r2) return true;
@@ -757,7 +762,7 @@ __device__ __forceinline__ void walk_step(WalkLane& w, const float4* __restrict_
     UFSTAT(ST_FINE_PAIRS, 1);
     if (!(lower < r2)) { UFSTAT(ST_REJECTS, 1); return; }
     // several local components: skip what is already one global component (a single-single pair was compared before it was queued)
-    if (!single && ufp_find_from(parent, la, pa) == ufp_find_from(parent, lb, pb)) return;
+    if (!single && (pa == pb || ufp_find_from(parent, la, pa) == ufp_find_from(parent, lb, pb))) return;
     bool hit = upper < r2;
     if (hit) UFSTAT(ST_ACCEPTS, 1);
     if (!hit) {
@@ -787,7 +792,7 @@ constexpr int UFF_THREADS = 128;
 constexpr int UFF_WARPS = UFF_THREADS / 32;
 constexpr int UFF_QUEUE = 128;  // per warp; stage 2 adds at most 96 per step to fewer than 32
 #ifndef UFF_MIN_BLOCKS
-#define UFF_MIN_BLOCKS 6
+#define UFF_MIN_BLOCKS 10
 #endif
 template <typename KT>
 __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const KT* __restrict__ ckey, const int4* __restrict__ crec,
@@ -870,10 +875,18 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
                     if (nb1 >= 0) pb1 = ld_cg(parent + rb1.z);
                     if (nb2 >= 0) pb2 = ld_cg(parent + rb2.z);
                 }
-                const int rootA = singleA ? ufp_find_from(parent, ra.z, pa) : -1;
-                if (nb0 >= 0 && !(singleA && ((unsigned)rb0.w >> 8) == 0u && ufp_find_from(parent, rb0.z, pb0) == rootA)) keep |= 1u;
-                if (nb1 >= 0 && !(singleA && ((unsigned)rb1.w >> 8) == 0u && ufp_find_from(parent, rb1.z, pb1) == rootA)) keep |= 2u;
-                if (nb2 >= 0 && !(singleA && ((unsigned)rb2.w >> 8) == 0u && ufp_find_from(parent, rb2.z, pb2) == rootA)) keep |= 4u;
+                // equal first hops already prove one component -- without touching the (hot) root of a large component; only the
+                // pairs that differ there walk up
+                unsigned undecided = 0;
+                if (nb0 >= 0) { if (!(singleA && ((unsigned)rb0.w >> 8) == 0u)) keep |= 1u; else if (pb0 != pa) undecided |= 1u; }
+                if (nb1 >= 0) { if (!(singleA && ((unsigned)rb1.w >> 8) == 0u)) keep |= 2u; else if (pb1 != pa) undecided |= 2u; }
+                if (nb2 >= 0) { if (!(singleA && ((unsigned)rb2.w >> 8) == 0u)) keep |= 4u; else if (pb2 != pa) undecided |= 4u; }
+                if (undecided) {
+                    const int rootA = ufp_find_from(parent, ra.z, pa);
+                    if ((undecided & 1u) && ufp_find_from(parent, rb0.z, pb0) != rootA) keep |= 1u;
+                    if ((undecided & 2u) && ufp_find_from(parent, rb1.z, pb1) != rootA) keep |= 2u;
+                    if ((undecided & 4u) && ufp_find_from(parent, rb2.z, pb2) != rootA) keep |= 4u;
+                }
                 UFSTAT(ST_CROSS_PAIRS, (nb0 >= 0) + (nb1 >= 0) + (nb2 >= 0));
                 UFSTAT(ST_ROOT_SKIPS, (nb0 >= 0) + (nb1 >= 0) + (nb2 >= 0) - __popc(keep));
             }
