@@ -9,7 +9,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no C++/torch types cross the boundary; nothing throws.
- *   - every function returns an int status: 0 = MOT_OK, negative = error (mot_last_error gives the text).
+ *   - every function returns an int status: 0 = MOT_OK, negative = error, positive = completed with a warning
+ *     (mot_last_error gives the text in both cases).
  *   - points are arrays of 4 floats (x, y, z, pad) == the memory layout of pcl::PointXYZ, so
  *     &cloud.points[0] is passed as-is ("xyz16").
  *   - input buffers are caller owned and only read; output buffers are caller owned, capacities are
@@ -38,7 +39,10 @@ enum {
     MOT_ERR_CAPACITY = -3,  /* input larger than the handle's max_points / output buffer too small */
     MOT_ERR_NO_MAP = -4,    /* removeStatic requested before mot_set_map (reference: map_init, MOT.cpp:128) */
     MOT_ERR_STATE = -5,     /* result query without a preceding clustering call / IHGP not configured */
-    MOT_ERR_NONFINITE = -6  /* NaN/Inf coordinate in a cloud passed to clustering (reference assumes is_dense) */
+    MOT_ERR_NONFINITE = -6, /* NaN/Inf coordinate in a cloud passed to clustering (reference assumes is_dense) */
+    /* positive = the call completed, with a condition the reference handles by carrying on (mot_last_error has the text) */
+    MOT_WARN_TRACKS_FULL = 1,    /* mot_tracks_step: max_tracks reached, some centroids were not registered (id -1, zero rows) */
+    MOT_WARN_VOXEL_OVERFLOW = 2  /* mot_voxel_grid: leaf too small for the extent; input returned unchanged, as PCL does */
 };
 
 /* Per-cluster table row (north_star: centroid / bbox per cluster; 40 bytes). */

@@ -150,7 +150,7 @@ class Tracker {
     }
 
     void check(int rc) {
-        if (rc != MOT_OK) throw std::runtime_error(std::string("mot_b200: ") + mot_last_error(h_) + " (code " + std::to_string(rc) + ")");
+        if (rc < 0) throw std::runtime_error(std::string("mot_b200: ") + mot_last_error(h_) + " (code " + std::to_string(rc) + ")");
     }
 
   private:

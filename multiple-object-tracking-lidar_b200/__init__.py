@@ -31,6 +31,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 MOT_OK = 0
+MOT_WARN_TRACKS_FULL = 1
+MOT_WARN_VOXEL_OVERFLOW = 2
 ERRORS = {-1: "MOT_ERR_INVALID", -2: "MOT_ERR_CUDA", -3: "MOT_ERR_CAPACITY", -4: "MOT_ERR_NO_MAP", -5: "MOT_ERR_STATE",
           -6: "MOT_ERR_NONFINITE"}
 
@@ -173,7 +175,9 @@ class Tracker:
             pass
 
     def _ck(self, rc):
-        if rc != MOT_OK:
+        """negative = error (raises); positive = completed with a warning (kept in self.last_warning)."""
+        self.last_warning = rc if rc > 0 else 0
+        if rc < 0:
             raise MotError(rc, self.lib.mot_last_error(self.h).decode())
 
     # -- configuration -------------------------------------------------------------------------------------

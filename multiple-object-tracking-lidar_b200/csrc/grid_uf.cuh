@@ -540,6 +540,10 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse(const
             const bool ok = mbar_wait_bounded(&sm.bar, parity);
             parity ^= 1u;
             staged = __all_sync(kFull, ok);
+            if (!staged) {  // the copy never landed: the barrier phase and the tile are in an unknown state -- report, do not guess
+                if (lane == 0) atomicOr(&d_counts[CNT_FLAGS], 8);
+                return;
+            }
         }
         __syncwarp();
         if (!staged) {
@@ -785,6 +789,10 @@ __global__ void __launch_bounds__(UFC_THREADS, UFC_MIN_BLOCKS) k_uf_sparse2(cons
             const bool ok = mbar_wait_bounded(&sm.bar, parity);
             parity ^= 1u;
             staged = __all_sync(kFull, ok);
+            if (!staged) {  // see k_uf_sparse
+                if (lane == 0) atomicOr(&d_counts[CNT_FLAGS], 8);
+                return;
+            }
         }
         __syncwarp();
         if (!staged) {

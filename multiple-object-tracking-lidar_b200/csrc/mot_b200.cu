@@ -473,6 +473,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     kc.idx_bits = ceil_log2(max_frame_len + 1);
     if (kc.idx_bits < 1) kc.idx_bits = 1;
     const int ckey_bits = kc.size_bits + kc.idx_bits + frame_bits;
+    if (ckey_bits > 64) return fail(h, MOT_ERR_INVALID, "cluster ordering key does not fit in 64 bits (max_cluster_size x points x frames too large)");
     int cgrid = (M + 255) / 256;
     if (cgrid > h->num_sms * 8) cgrid = h->num_sms * 8;
     LAUNCH(KID_COMP_ACC, k_comp_accumulate<<<cgrid, 256, 0, st>>>(h->d_fc_start, h->d_root, h->d_csize, h->d_cmin, h->d_counts));
@@ -487,6 +488,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_total = total;
     std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
+    if (h->h_pinned[8 + CNT_FLAGS] & 8) return fail(h, MOT_ERR_CUDA, "TMA staging of a cell tile timed out (mbarrier never completed)");
     if (h->h_pinned[8 + CNT_FLAGS] & 4) return fail(h, MOT_ERR_CAPACITY, "cell-pair task list overflow (internal capacity)");
     if (h->h_pinned[8 + CNT_FLAGS] & 2) return fail(h, MOT_ERR_CUDA, "radix sort look-back exceeded its spin limit");
     h->res_fine = h->h_pinned[8 + CNT_FINE];
@@ -935,7 +937,14 @@ static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx
         const int maxb = (int)std::floor(mx * vp.inv[d]);                                  // max_b_
         div[d] = (long long)maxb - vp.minb[d] + 1;                                         // div_b_
     }
-    if (div[0] * div[1] * div[2] > 0x7fffffffll) return fail(h, MOT_ERR_INVALID, "leaf size too small for the cloud extent (voxel index overflows, as in PCL)");
+    if (div[0] * div[1] * div[2] > 0x7fffffffll) {
+        // pcl::VoxelGrid::applyFilter: "Leaf size is too small for the input dataset. Integer indices would overflow." -- PCL
+        // warns and hands the input cloud back unchanged; so does this call (status MOT_WARN_VOXEL_OVERFLOW)
+        CK(cudaMemcpyAsync(h->d_pts, d_src, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+        *m_out = n;
+        h->err = "leaf size too small for the cloud extent: voxel index overflows, input returned unchanged (as PCL does)";
+        return MOT_WARN_VOXEL_OVERFLOW;
+    }
     vp.mul1 = (int)div[0];
     vp.mul2 = (int)(div[0] * div[1]);
     uint32_t* keys[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
@@ -971,7 +980,8 @@ int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, fl
     CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyDefault, h->stream));
     int V = 0;
     rc = voxel_grid_device(h, h->d_in, (int)n, leaf_x, leaf_y, leaf_z, &V);
-    if (rc != MOT_OK) return rc;
+    if (rc < 0) return rc;
+    const int warn = rc;
     *m = (size_t)V;
     if (out_xyz16) {
         if (out_capacity < (size_t)V) return fail(h, MOT_ERR_CAPACITY, "output cloud buffer too small");
@@ -979,7 +989,7 @@ int mot_voxel_grid(mot_handle* h, const float* xyz16, size_t n, float leaf_x, fl
     }
     CK(mot_sync(h));
     fold_profile(h);
-    return MOT_OK;
+    return warn;
 }
 
 // PointCloud2 wire format -> pcl::PointXYZ on the device (pcl::fromROSMsg, MOT.cpp:448-449).
@@ -987,8 +997,9 @@ int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, 
                            uint32_t off_z, int is_bigendian, int drop_nonfinite, float* out_xyz16, size_t out_capacity, size_t* m) {
     int rc = check_frame_args(h, data, n_points);
     if (rc != MOT_OK) return rc;
-    if (!m || point_step < 12 || off_x + 4 > point_step || off_y + 4 > point_step || off_z + 4 > point_step)
+    if (!m || point_step < 12 || (uint64_t)off_x + 4 > point_step || (uint64_t)off_y + 4 > point_step || (uint64_t)off_z + 4 > point_step)
         return fail(h, MOT_ERR_INVALID, "bad PointCloud2 layout");
+    if (n_points > SIZE_MAX / point_step) return fail(h, MOT_ERR_INVALID, "PointCloud2 payload size overflows");
     CK(cudaSetDevice(h->device));
     *m = 0;
     if (n_points == 0) return MOT_OK;
@@ -1457,16 +1468,23 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
     CK(mot_sync(h));
     h->trk_n = h->h_pinned[32 + TM_NTRACKS];
     if (n_tracks) *n_tracks = h->trk_n;
-    if (h->h_pinned[32 + TM_OVERFLOW]) return fail(h, MOT_ERR_CAPACITY, "track table full (max_tracks)");
+    // A full track table is not fatal (the reference has no cap): the centroids that found no slot are skipped (id -1, zero
+    // rows), everything else -- filtering, the callback counter, the purge that frees slots -- runs as usual.
+    const int dropped = h->h_pinned[32 + TM_OVERFLOW];
+    if (dropped) h->err = "track table full (max_tracks): " + std::to_string(dropped) + " centroid(s) not registered";
     if (this_obj_ids) CK(cudaMemcpyAsync(this_obj_ids, h->d_ent_ids, (size_t)K * sizeof(int), cudaMemcpyDefault, st));
     if (h->trk_first) {
         h->trk_first = false;
         CK(mot_sync(h));
         fold_profile(h);
-        return MOT_OK;
+        return dropped ? MOT_WARN_TRACKS_FULL : MOT_OK;
     }
     // callIHGP over this_objIDs (MOT.cpp:621-662); a track that was matched twice in this frame is filtered twice, in order
     const int max_occ = h->h_pinned[32 + TM_MAX_OCC];
+    if (dropped) {
+        CK(cudaMemsetAsync(h->d_posvel, 0, (size_t)K * 2 * sizeof(float4), st));
+        CK(cudaMemsetAsync(h->d_obstacles, 0, (size_t)K * sizeof(ObstacleRow), st));
+    }
     const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (K + IHGP_WARPS - 1) / IHGP_WARPS;
@@ -1493,7 +1511,7 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
     if (n_tracks) *n_tracks = h->trk_n;
     if (produced) *produced = 1;
     fold_profile(h);
-    return MOT_OK;
+    return dropped ? MOT_WARN_TRACKS_FULL : MOT_OK;
 }
 
 int mot_tracks_get(mot_handle* h, int32_t* ids, float* rings, double* m_state, size_t capacity, int32_t* n_tracks) {

@@ -30,7 +30,10 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_associate(const float4* __res
                                                               int* __restrict__ occurrence) {
     __shared__ int s_best[ASSOC_THREADS / 32];
     __shared__ int s_n;
-    if (threadIdx.x == 0) s_n = meta[TM_NTRACKS];
+    if (threadIdx.x == 0) {
+        s_n = meta[TM_NTRACKS];
+        meta[TM_OVERFLOW] = 0;  // centroids dropped by THIS call because the table was full (the purge may free slots later)
+    }
     for (int t = threadIdx.x; t < max_tracks; t += ASSOC_THREADS) seen[t] = 0;
     __syncthreads();
     int max_occ = 0;
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(ASSOC_THREADS) k_associate(const float4* __res
                 s_n = n + 1;
             } else {
                 slot = -1;  // track table full: reported to the host, the centroid is skipped
-                meta[TM_OVERFLOW] = 1;
+                meta[TM_OVERFLOW] += 1;
                 this_ids[k] = -1;
             }
             slot_of_entry[k] = slot;

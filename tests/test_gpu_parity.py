@@ -446,6 +446,55 @@ def test_tracks_association_lifecycle(mot, oracle, seed, L):
     t.close()
 
 
+def test_voxel_grid_index_overflow_passes_input_through(mot):
+    # pcl::VoxelGrid::applyFilter warns and returns the input cloud when the voxel index would overflow an int
+    t = mot.Tracker(device=0, max_points=4096, max_tracks=0)
+    rng = np.random.default_rng(3)
+    pts = np.ones((1000, 4), np.float32)
+    pts[:, :3] = rng.uniform(-5000, 5000, (1000, 3))
+    out = t.voxel_grid(pts, (0.001, 0.001, 0.001))
+    assert t.last_warning == mot.MOT_WARN_VOXEL_OVERFLOW
+    assert np.array_equal(out, pts)
+    out = t.voxel_grid(pts, (50.0, 50.0, 50.0))
+    assert t.last_warning == 0 and 0 < len(out) < len(pts)
+    t.close()
+
+
+def test_tracks_table_full_is_not_fatal(mot, oracle):
+    # the reference has no track cap; when max_tracks is reached the extra centroids are skipped (id -1, zero
+    # rows, warning status) while filtering, the callback counter and the purge keep running -- so the table drains again
+    from oracle.tracker_ref import TrackerRef
+    hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
+    freq, thr, L, T = 10.0, 0.4, 10, 8
+    t = mot.Tracker(device=0, max_points=1024, max_tracks=T)
+    t.ihgp_configure(0.1, 0.03, hyp, hyp, L)
+    ref = TrackerRef(freq, thr, L, 0.03, hyp, hyp)
+
+    def cen(n, now, x0=0.0):
+        return np.array([[x0 + 3.0 * i, 1.0, 0.0, now] for i in range(n)], dtype=np.float32)
+
+    now = 0.0
+    out = t.tracks_step(cen(T, now), now, thr, freq)          # first frame: fills the table exactly
+    ref.step(cen(T, now), now)
+    assert t.last_warning == 0 and out["n_tracks"] == T
+    for f in range(1, 4):                                      # T known objects + 3 new ones that cannot be registered
+        now = 0.1 * f
+        c = np.concatenate([cen(T, now), cen(3, now, x0=100.0)])
+        out = t.tracks_step(c, now, thr, freq)
+        assert t.last_warning == mot.MOT_WARN_TRACKS_FULL
+        r_ids, r_pv = ref.step(cen(T, now), now)               # the reference run only sees what could be registered
+        assert out["produced"] and out["n_tracks"] == T
+        assert np.array_equal(out["ids"][:T], r_ids) and (out["ids"][T:] == -1).all()
+        np.testing.assert_allclose(out["pos_vel"][:T], r_pv, rtol=RTOL, atol=1e-6)   # matched tracks were filtered as usual
+        assert not out["pos_vel"][T:].any()
+    # the old objects disappear; after the purge period (5 s at 10 Hz = 51 callbacks) their slots are free again
+    for f in range(4, 4 + 60):
+        now = 0.1 * f
+        out = t.tracks_step(cen(2, now, x0=100.0), now, thr, freq)
+    assert t.last_warning == 0 and out["n_tracks"] <= 3 and (out["ids"] >= 0).all()
+    t.close()
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("MOT_FUZZ_SEEDS", "12"))))
 def test_fuzz_partition_vs_oracle(trk, oracle, seed):
     # randomised differential test: mixtures of dense blobs, planes, lines and uniform noise at random scales / tolerances;
