@@ -191,12 +191,52 @@ int mot_host_unregister(void* ptr);
 /* ---- frame batches (BASELINE config 3: multi-LiDAR / multi-sequence streams).  n_frames clouds are
  * concatenated in xyz16; frame f owns points [frame_offsets[f], frame_offsets[f+1]).  Frames never share
  * clusters.  cluster c belongs to frame f iff frame_cluster_offsets[f] <= c < frame_cluster_offsets[f+1];
- * point_indices are positions inside the owning frame's cloud.  No removeStatic (apply it per frame).
+ * point_indices are positions inside the owning frame's cloud.  Clustering only; mot_frame_batch is the full path.
  * mot_cluster_stats / mot_result_fetch give the per-cluster table of the whole batch (same cluster order). */
 int mot_cluster_batch(mot_handle* h, const float* xyz16, const int64_t* frame_offsets, int n_frames,
                       int32_t* frame_cluster_offsets /* n_frames+1 */, int32_t* cluster_offsets,
                       size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters);
 int mot_cluster_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames);
+
+/* The whole per-frame path on a batch (BASELINE config 3 with the map): removeStatic with the handle's map (optional) ->
+ * clustering -> table (+ circumcentres when centroids_xyzi != NULL).  What ObstacleTrack::clusterPointCloud (MOT.cpp:461-491)
+ * does for one cloud, for n_frames clouds in one pass.  xyz: concatenated clouds, point_stride_bytes = 16 (pcl::PointXYZ)
+ * or 12 (packed x, y, z: a quarter fewer PCIe bytes, expanded on the device).  frame_stamps (optional, n_frames floats) are
+ * the centroid intensities (stamp - time_init per frame, MOT.cpp:491).  frame_kept_offsets (optional, n_frames+1): boundaries
+ * of the frames inside the kept cloud after removeStatic; point_indices are positions inside the owning frame's kept cloud.
+ * Output pointers may be host or device pointers. */
+int mot_frame_batch(mot_handle* h, const float* xyz, int point_stride_bytes, const int64_t* frame_offsets, int n_frames,
+                    int do_remove_static, const float* frame_stamps, int32_t* frame_kept_offsets,
+                    int32_t* frame_cluster_offsets, int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices,
+                    size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats, float* centroids_xyzi,
+                    size_t table_capacity);
+/* Same with the clouds already on the device (16-byte points); results stay on the device (mot_result_*). */
+int mot_frame_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames, int do_remove_static,
+                           int with_centroids, const float* frame_stamps);
+
+/* the same batch call over several handles = several GPUs of one box (one handle per GPU; more than one handle on
+ * a GPU overlaps one range's copies with another's kernels).  One host thread per handle; handle g takes the contiguous frame
+ * range [n_frames*g/n, n_frames*(g+1)/n); there is no exchange between the ranges.  The merged tables land in the caller's
+ * buffers -- host memory, or device memory of any GPU (the copies are cudaMemcpyDefault) -- in frame order, exactly as one
+ * mot_frame_batch call over all frames would leave them.  Every handle must hold the same map / parameters.  The handles'
+ * own results are consumed by the merge. */
+int mot_batch_run(mot_handle* const* handles, int n_handles, const float* xyz, int point_stride_bytes, const int64_t* frame_offsets,
+                  int n_frames, int do_remove_static, const float* frame_stamps, int32_t* frame_kept_offsets,
+                  int32_t* frame_cluster_offsets, int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices,
+                  size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats, float* centroids_xyzi,
+                  size_t table_capacity);
+
+/* ObstacleTrack::clusterPointCloud in one call (MOT.cpp:444-505): pcl::fromROSMsg (:448-449) -> VoxelGrid with leaf
+ * (L, L, 20 L) (:452-456, skipped when voxel_leaf_size <= 0) -> removeStatic (:461, optional) -> EuclideanClusterExtraction
+ * (:472-488) -> getCentroid (:491, when centroids_xyzi != NULL).  The cloud never returns to the host between the stages
+ * (only the stage sizes do).  data: the PointCloud2 payload (host or device pointer); non-finite points are dropped after the
+ * unpack, as PCL's filters do for a non-dense cloud.  kept_xyz16 (optional) receives the cloud that was clustered; indices
+ * refer to it. */
+int mot_cluster_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y,
+                            uint32_t off_z, int is_bigendian, float voxel_leaf_size, int do_remove_static,
+                            double stamp_minus_time_init, float* kept_xyz16, size_t kept_capacity, size_t* m,
+                            int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity,
+                            int32_t* n_clusters, mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity);
 
 /* ---- IHGP track filter.  Replaces Matern32model + InfiniteHorizonGP construction in
  * registerNewObstacle (MOT.cpp:521-534; IHGP.cpp:12-37; M32.cpp:15-24): hyp = {sigma2, magnSigma2,

@@ -117,6 +117,14 @@ SYMBOLS = {
     "mot_host_unregister": (C.c_int, [C.c_void_p]),
     "mot_cluster_batch": (C.c_int, [_H, C.c_void_p, _i64, C.c_int, C.c_void_p, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),
     "mot_cluster_batch_device": (C.c_int, [_H, C.c_void_p, _i64, C.c_int]),
+    "mot_frame_batch": (C.c_int, [_H, C.c_void_p, C.c_int, _i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _SIZE, C.c_void_p, _SIZE,
+                                  C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, _SIZE]),
+    "mot_frame_batch_device": (C.c_int, [_H, C.c_void_p, _i64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "mot_batch_run": (C.c_int, [C.POINTER(_H), C.c_int, C.c_void_p, C.c_int, _i64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _SIZE,
+                                C.c_void_p, _SIZE, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, _SIZE]),
+    "mot_cluster_pointcloud2": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_double,
+                                          C.c_void_p, _SIZE, C.POINTER(_SIZE), C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.POINTER(C.c_int32), C.c_void_p,
+                                          C.c_void_p, _SIZE]),
     "mot_ihgp_configure": (C.c_int, [_H, C.c_double, C.c_float, _f64, _f64, C.c_int]),
     "mot_ihgp_constants": (C.c_int, [_H, C.c_int, _f64]),
     "mot_ihgp_step": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -351,6 +359,34 @@ class Tracker:
         K = k.value
         return fco, off[: K + 1].copy(), idx[: off[K]].copy()
 
+    def frame_batch(self, clouds, do_remove_static=False, stamps=None, want_stats=True, want_centroids=True, packed12=False):
+        """mot_frame_batch: the whole per-frame path (removeStatic -> extract -> tables) on a list of clouds.  Returns a dict."""
+        return frame_batch_call(self.lib, None, self, clouds, do_remove_static, stamps, want_stats, want_centroids, packed12)
+
+    def frame_batch_device(self, d_ptr, frame_offsets, do_remove_static=False, with_centroids=False, stamps=None):
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        st = np.ascontiguousarray(stamps, dtype=np.float32) if stamps is not None else None
+        self._ck(self.lib.mot_frame_batch_device(self.h, C.c_void_p(int(d_ptr)), fo, len(fo) - 1, int(do_remove_static), int(with_centroids), _ptr(st)))
+
+    def cluster_pointcloud2(self, data, n_points, point_step, off_xyz, is_bigendian=False, voxel_leaf_size=0.0, do_remove_static=False,
+                            stamp_minus_time_init=0.0, want_centroids=True):
+        """ObstacleTrack::clusterPointCloud in one call (reference MOT.cpp:444-505).  Returns a dict like frame()."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        n = int(n_points)
+        kept = np.empty((max(n, 1), 4), dtype=np.float32)
+        off = np.empty(n + 1, dtype=np.int32)
+        idx = np.empty(max(n, 1), dtype=np.int32)
+        st = np.zeros(max(n, 1), dtype=STAT_DTYPE)
+        cen = np.zeros((max(n, 1), 4), dtype=np.float32) if want_centroids else None
+        m, k = _SIZE(0), C.c_int32(0)
+        self._ck(self.lib.mot_cluster_pointcloud2(self.h, _ptr(data), n, int(point_step), int(off_xyz[0]), int(off_xyz[1]), int(off_xyz[2]),
+                                                  int(is_bigendian), np.float32(voxel_leaf_size), int(do_remove_static), float(stamp_minus_time_init),
+                                                  _ptr(kept), len(kept), C.byref(m), _ptr(off), len(off), _ptr(idx), len(idx), C.byref(k), _ptr(st),
+                                                  _ptr(cen), max(n, 1)))
+        K, M = k.value, m.value
+        return dict(m=M, K=K, kept=kept[:M], offsets=off[: K + 1].copy(), indices=idx[: off[K]].copy(), stats=st[:K].copy(),
+                    centroids=cen[:K].copy() if want_centroids else None)
+
     def cluster_batch_device(self, d_ptr, frame_offsets):
         fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
         self._ck(self.lib.mot_cluster_batch_device(self.h, C.c_void_p(int(d_ptr)), fo, len(fo) - 1))
@@ -414,6 +450,39 @@ class Tracker:
         ids = np.ascontiguousarray(track_ids, dtype=np.int32) if track_ids is not None else None
         self._ck(self.lib.mot_ihgp_step_obstacles(self.h, _ptr(rings), T, _ptr(ids), _ptr(m_state), _ptr(out), _ptr(obs)))
         return out, obs[:T]
+
+
+def frame_batch_call(lib, handles, trk, clouds, do_remove_static, stamps, want_stats, want_centroids, packed12):
+    """Shared by Tracker.frame_batch (one handle) and batch_run (several handles / GPUs)."""
+    F = len(clouds)
+    fo = np.zeros(F + 1, dtype=np.int64)
+    fo[1:] = np.cumsum([len(c) for c in clouds])
+    total = int(fo[-1])
+    allp = _cloud(np.concatenate([_cloud(c) for c in clouds])) if total else np.zeros((0, 4), np.float32)
+    src = np.ascontiguousarray(allp[:, :3]) if packed12 else allp
+    fko = np.zeros(F + 1, dtype=np.int32)
+    fco = np.zeros(F + 1, dtype=np.int32)
+    off = np.empty(total + 1, dtype=np.int32)
+    idx = np.empty(max(total, 1), dtype=np.int32)
+    st = np.zeros(max(total, 1), dtype=STAT_DTYPE) if want_stats else None
+    cen = np.zeros((max(total, 1), 4), dtype=np.float32) if want_centroids else None
+    stp = np.ascontiguousarray(stamps, dtype=np.float32) if stamps is not None else None
+    k = C.c_int32(0)
+    tail = (_ptr(src), 12 if packed12 else 16, fo, F, int(do_remove_static), _ptr(stp), _ptr(fko), _ptr(fco), _ptr(off), len(off), _ptr(idx), len(idx),
+            C.byref(k), _ptr(st), _ptr(cen), max(total, 1))
+    if handles is None:
+        trk._ck(lib.mot_frame_batch(trk.h, *tail))
+    else:
+        arr = (_H * len(handles))(*[t.h for t in handles])
+        handles[0]._ck(lib.mot_batch_run(arr, len(handles), *tail))
+    K = k.value
+    return dict(K=K, frame_kept_offsets=fko, frame_cluster_offsets=fco, offsets=off[: K + 1].copy(), indices=idx[: off[K]].copy(),
+                stats=st[:K].copy() if want_stats else None, centroids=cen[:K].copy() if want_centroids else None)
+
+
+def batch_run(trackers, clouds, do_remove_static=False, stamps=None, want_stats=True, want_centroids=True, packed12=False):
+    """mot_batch_run: the frames of `clouds` sharded over the handles in `trackers` (one per GPU, or several per GPU)."""
+    return frame_batch_call(trackers[0].lib, list(trackers), None, clouds, do_remove_static, stamps, want_stats, want_centroids, packed12)
 
 
 from . import synth  # noqa: E402,F401

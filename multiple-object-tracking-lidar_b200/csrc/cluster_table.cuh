@@ -451,7 +451,9 @@ __global__ void __launch_bounds__(FP_THREADS) k_farthest_pair(const float4* __re
 constexpr int CC_THREADS = 128;
 __global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
                                                               const uint32_t* __restrict__ indices, int K, int slabs,
-                                                              const PairCand* __restrict__ cands, float intensity, float4* __restrict__ out) {
+                                                              const PairCand* __restrict__ cands, float intensity, float4* __restrict__ out,
+                                                              const float* __restrict__ frame_stamps = nullptr,
+                                                              const int* __restrict__ frame_cl_offsets = nullptr, int n_frames = 1) {
     __shared__ float sdist[CC_THREADS / 32];
     __shared__ int sk[CC_THREADS / 32];
     for (int c = blockIdx.x; c < K; c += gridDim.x) {
@@ -519,6 +521,14 @@ __global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __res
             }
             o.z = 0.0f;
             o.w = intensity;
+            if (frame_stamps) {  // batch: the stamp of the frame that owns cluster c (largest f with frame_cl_offsets[f] <= c)
+                int lo = 0, hi = n_frames - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (frame_cl_offsets[mid] <= c) lo = mid; else hi = mid - 1;
+                }
+                o.w = frame_stamps[lo];
+            }
             out[c] = o;
         }
         __syncthreads();

@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mot_b200.h"
@@ -54,12 +55,12 @@ enum KernelId {
     KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
-    "k_rs_count", "k_rs_compact", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
+    "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
     "k_hash_clear", "k_cells_write", "k_uf_pairs<1>", "k_uf_flatten<in-place>", "k_uf_pairs<2>", "k_uf_flatten<root>", "k_coarse_records", "k_uf_sparse", "k_uf_dense<1>", "k_uf_dense<2>", "k_comp_accumulate", "k_kept_list",
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_pc2_compact", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused"};
 
 struct mot_handle {
     int device = 0;
@@ -103,7 +104,13 @@ struct mot_handle {
     uint64_t* d_ckeys[2] = {nullptr, nullptr};
     uint32_t* d_croots[2] = {nullptr, nullptr};
     int* d_cl_offsets = nullptr;
-    int* d_frame_offsets = nullptr;
+    int* d_frame_offsets = nullptr;   // frame boundaries of the cloud being clustered (batch mode)
+    int* d_frame_offsets_in = nullptr;  // ... of the input cloud, before removeStatic
+    unsigned* d_c1p_status = nullptr;  // one-pass compaction: tile status words + ticket
+    size_t c1p_tiles = 0;
+    int rs_mode = 1;  // 1: single-pass compaction (decoupled look-back); 0: count + compact (MOT_RS_MODE)
+    float* d_frame_stamps = nullptr;  // per-frame centroid intensity (batch mode)
+    bool have_frame_stamps = false;
     int* d_frame_cl_offsets = nullptr;
     size_t frame_capacity = 0;
     ClusterStat* d_stats = nullptr;
@@ -134,6 +141,7 @@ struct mot_handle {
     PairCand* d_cands = nullptr;
     size_t table_capacity = 0, cand_capacity = 0;
     int* h_pinned = nullptr;  // 32 ints: counts + bbox readback
+    int* h_pinned_fo = nullptr;  // pinned staging of a batch's frame offsets (+ stamps)
 
     // IHGP
     bool ihgp_ready = false;
@@ -245,15 +253,45 @@ int ensure_tables(mot_handle* h, size_t K, size_t cands) {
 // ------------------------------------------------------------------------------------------------------------
 // removeStatic stage: d_src[n] -> d_pts[M], M and bbox left in device memory (read at S1 by cluster_core)
 // ------------------------------------------------------------------------------------------------------------
-int enqueue_remove_static(mot_handle* h, const float4* d_src, int n) {
-    const Chunking ck = make_chunking(n, RSK_THREADS, RSK_MAX_GRID);
+// d_src[n] -> d_dst[M] (stable); M is left in d_counts[CNT_M], the bbox of the kept points in d_bbox.  In batch mode
+// (n_frames > 1) the frame boundaries d_frame_offsets_in are mapped to the compacted cloud (d_frame_offsets).
+int enqueue_remove_static(mot_handle* h, const float4* d_src, int n, float4* d_dst, int n_frames = 1) {
     const size_t bitmap_bytes = (size_t)((h->mp.n_words * 4 + 15) & ~15);
     const int use_smem = bitmap_bytes <= (size_t)RSK_SMEM_BITMAP_MAX ? 1 : 0;
     const size_t smem = use_smem ? bitmap_bytes : 0;
-    LAUNCH(KID_RS_COUNT, k_rs_count<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_bbox));
-    LAUNCH(KID_RS_COMPACT, k_rs_compact<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk,
-                                                                                  h->d_pts, h->d_counts + CNT_M));
+    if (h->rs_mode == 1) {
+        const int tiles = (n + C1P_TILE - 1) / C1P_TILE;
+        CK(cudaMemsetAsync(h->d_c1p_status, 0, ((size_t)tiles + 1) * sizeof(unsigned), h->stream));
+        LAUNCH(KID_RS_COMPACT, k_compact_onepass<0><<<tiles, C1P_THREADS, smem, h->stream>>>(d_src, n, h->mp, h->d_bits, use_smem, d_dst, h->d_c1p_status, tiles,
+                                                                                          h->d_counts + CNT_M, h->d_bbox,
+                                                                                          n_frames > 1 ? h->d_frame_offsets_in : nullptr, n_frames,
+                                                                                          n_frames > 1 ? h->d_frame_offsets : nullptr,
+                                                                                          h->d_counts + CNT_FLAGS));
+    } else {
+        if (n_frames > 1) return fail(h, MOT_ERR_STATE, "MOT_RS_MODE=0 does not support removeStatic on frame batches");
+        const Chunking ck = make_chunking(n, RSK_THREADS, RSK_MAX_GRID);
+        LAUNCH(KID_RS_COUNT, k_rs_count<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk, h->d_bbox));
+        LAUNCH(KID_RS_COMPACT, k_rs_compact<<<ck.grid, RSK_THREADS, smem, h->stream>>>(d_src, n, ck.chunk, h->mp, h->d_bits, use_smem, h->d_blk,
+                                                                                      d_dst, h->d_counts + CNT_M));
+    }
     CK(cudaGetLastError());
+    return MOT_OK;
+}
+
+int ensure_raw(mot_handle* h, size_t bytes) {
+    if (bytes > h->raw_capacity) {
+        if (h->d_raw) cudaFree(h->d_raw);
+        h->d_raw = nullptr;
+        h->raw_capacity = 0;
+        CK(cudaMalloc(reinterpret_cast<void**>(&h->d_raw), bytes + 256));
+        h->raw_capacity = bytes;
+    }
+    return MOT_OK;
+}
+
+static const int kBboxInit[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
+int reset_bbox(mot_handle* h) {
+    CK(cudaMemcpyAsync(h->d_bbox, kBboxInit, sizeof(kBboxInit), cudaMemcpyHostToDevice, h->stream));
     return MOT_OK;
 }
 
@@ -522,7 +560,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     // ---- K7 / K8 (on global point indices; batch indices are made frame-local afterwards) ----
     if (K > 0) {
         int slabs = 1;
-        const bool cent = with_centroids && n_frames == 1;
+        const bool cent = with_centroids;
         if (cent && K < 2000) {
             slabs = (h->num_sms * 16 + K - 1) / K;
             if (slabs > 64) slabs = 64;
@@ -540,7 +578,9 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
             LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
                                                                                        h->d_cands));
             LAUNCH(KID_CIRCUMCENTRE, k_circumcentre<<<sgrid, CC_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
-                                                                                 h->d_cands, (float)stamp, h->d_centroids));
+                                                                                 h->d_cands, (float)stamp, h->d_centroids,
+                                                                                 n_frames > 1 && h->have_frame_stamps ? h->d_frame_stamps : nullptr,
+                                                                                 h->d_frame_cl_offsets, n_frames));
             h->res_centroids = true;
         }
     }
@@ -761,7 +801,13 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_bbox, (size_t)8));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));
         h->frame_capacity = 4096;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned_fo), (2 * h->frame_capacity + 8) * sizeof(int), cudaHostAllocDefault));
         CK(dalloc(&h->d_frame_offsets, h->frame_capacity + 2));
+        CK(dalloc(&h->d_frame_offsets_in, h->frame_capacity + 2));
+        CK(dalloc(&h->d_frame_stamps, h->frame_capacity + 2));
+        h->c1p_tiles = (n + C1P_TILE - 1) / C1P_TILE;
+        CK(dalloc(&h->d_c1p_status, h->c1p_tiles + 2));
+        if (const char* e = getenv("MOT_RS_MODE")) h->rs_mode = atoi(e);
         CK(dalloc(&h->d_frame_cl_offsets, h->frame_capacity + 2));
         CK(cudaMemset(h->d_frame_offsets, 0, (h->frame_capacity + 2) * sizeof(int)));
         for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -777,6 +823,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(cudaFuncSetAttribute(k_clusters_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMALL_SMEM));
         CK(cudaFuncSetAttribute(k_rs_count, cudaFuncAttributeMaxDynamicSharedMemorySize, RSK_SMEM_BITMAP_MAX));
         CK(cudaFuncSetAttribute(k_rs_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, RSK_SMEM_BITMAP_MAX));
+        CK(cudaFuncSetAttribute(k_compact_onepass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSK_SMEM_BITMAP_MAX));
         if (max_tracks > 0) {
             CK(dalloc(&h->d_mstate, max_tracks * 4));
             CK(dalloc(&h->d_posvel, max_tracks * 2));
@@ -813,13 +860,14 @@ int mot_destroy(mot_handle* h) {
     void* ptrs[] = {h->d_in, h->d_pts, h->d_spts, h->d_keys[0], h->d_keys[1], h->d_vals[0], h->d_vals[1], h->d_ckeys[0], h->d_ckeys[1],
                     h->d_croots[0], h->d_croots[1], h->d_fc_start, h->d_cc_first, h->d_parent, h->d_root, h->d_csize, h->d_cmin,
                     h->d_crank, h->d_labels, h->d_cl_offsets, h->d_hkeys, h->d_hvals, h->rws.hist, h->rws.prefix, h->rws.tot, h->rws.ghist, h->rws.status, h->d_blk,
-                    h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
+                    h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_offsets_in, h->d_frame_stamps, h->d_c1p_status, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
                     h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
                     h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_pinned_fo) cudaFreeHost(h->h_pinned_fo);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->timer_ev)
@@ -900,7 +948,7 @@ int mot_remove_static(mot_handle* h, const float* xyz16, size_t n, float* out_xy
     rc = reset_frame_state(h);
     if (rc != MOT_OK) return rc;
     CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
-    rc = enqueue_remove_static(h, h->d_in, (int)n);
+    rc = enqueue_remove_static(h, h->d_in, (int)n, h->d_pts);
     if (rc != MOT_OK) return rc;
     CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(mot_sync(h));
@@ -937,7 +985,7 @@ static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx
         const int maxb = (int)std::floor(mx * vp.inv[d]);                                  // max_b_
         div[d] = (long long)maxb - vp.minb[d] + 1;                                         // div_b_
     }
-    if (div[0] * div[1] * div[2] > 0x7fffffffll) {
+    if ((double)div[0] * (double)div[1] * (double)div[2] > 2147483647.0) {  // (the int64 product itself can wrap)
         // pcl::VoxelGrid::applyFilter: "Leaf size is too small for the input dataset. Integer indices would overflow." -- PCL
         // warns and hands the input cloud back unchanged; so does this call (status MOT_WARN_VOXEL_OVERFLOW)
         CK(cudaMemcpyAsync(h->d_pts, d_src, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
@@ -1006,13 +1054,8 @@ int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, 
     rc = reset_frame_state(h);
     if (rc != MOT_OK) return rc;
     const size_t bytes = n_points * (size_t)point_step;
-    if (bytes > h->raw_capacity) {
-        if (h->d_raw) cudaFree(h->d_raw);
-        h->d_raw = nullptr;
-        h->raw_capacity = 0;
-        CK(cudaMalloc(reinterpret_cast<void**>(&h->d_raw), bytes + 256));
-        h->raw_capacity = bytes;
-    }
+    rc = ensure_raw(h, bytes);
+    if (rc != MOT_OK) return rc;
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->d_raw, data, bytes, cudaMemcpyDefault, st));
     const int n = (int)n_points;
@@ -1021,7 +1064,11 @@ int mot_unpack_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, 
     const float4* result = h->d_in;
     size_t M = n_points;
     if (drop_nonfinite) {
-        LAUNCH(KID_PC2_COMPACT, k_pc2_compact<<<ck.grid, 256, 0, st>>>(h->d_in, n, ck.chunk, h->d_blk, h->d_pts, h->d_counts + CNT_M));
+        const int tiles = (n + C1P_TILE - 1) / C1P_TILE;
+        CK(cudaMemsetAsync(h->d_c1p_status, 0, ((size_t)tiles + 1) * sizeof(unsigned), st));
+        LAUNCH(KID_PC2_COMPACT, k_compact_onepass<1><<<tiles, C1P_THREADS, 0, st>>>(h->d_in, n, h->mp, nullptr, 0, h->d_pts, h->d_c1p_status, tiles,
+                                                                                 h->d_counts + CNT_M, h->d_bbox, nullptr, 1, nullptr,
+                                                                                 h->d_counts + CNT_FLAGS));
         CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(mot_sync(h));
         M = (size_t)h->h_pinned[8 + CNT_M];
@@ -1064,10 +1111,12 @@ int mot_cluster_stats(mot_handle* h, mot_cluster_stat* stats, size_t capacity) {
 int mot_get_centroid(mot_handle* h, double stamp_minus_time_init, float* out_xyzi, size_t capacity) {
     if (!h || !out_xyzi) return h ? fail(h, MOT_ERR_INVALID, "null output") : MOT_ERR_INVALID;
     if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
-    if (h->res_frames != 1) return fail(h, MOT_ERR_STATE, "centroids are not produced in batch mode");
+    if (h->res_frames != 1 && !h->res_centroids) return fail(h, MOT_ERR_STATE, "batch centroids must be requested with the batch call (indices are frame-local afterwards)");
     CK(cudaSetDevice(h->device));
-    int rc = compute_centroids_late(h, stamp_minus_time_init);
-    if (rc != MOT_OK) return rc;
+    if (h->res_frames == 1) {
+        int rc = compute_centroids_late(h, stamp_minus_time_init);
+        if (rc != MOT_OK) return rc;
+    }
     return fetch_result(h, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, out_xyzi, capacity);
 }
 
@@ -1081,7 +1130,7 @@ int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remov
     CK(cudaEventRecord(h->ev[0], h->stream));
     const float4* src = reinterpret_cast<const float4*>(d_xyz16);
     if (do_remove_static && n > 0) {
-        rc = enqueue_remove_static(h, src, (int)n);
+        rc = enqueue_remove_static(h, src, (int)n, h->d_pts);
         if (rc != MOT_OK) return rc;
         rc = cluster_core(h, h->d_pts, -1, 1, with_centroids != 0, stamp);
     } else {
@@ -1103,7 +1152,7 @@ int mot_frame(mot_handle* h, const float* xyz16, size_t n, double stamp, float* 
     CK(cudaEventRecord(h->ev[0], h->stream));
     if (n) {
         CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
-        rc = enqueue_remove_static(h, h->d_in, (int)n);
+        rc = enqueue_remove_static(h, h->d_in, (int)n, h->d_pts);
         if (rc != MOT_OK) return rc;
         rc = cluster_core(h, h->d_pts, -1, 1, centroids_xyzi != nullptr, stamp);
     } else {
@@ -1239,12 +1288,14 @@ int mot_timer_stop(mot_handle* h, float* ms) {
 }
 
 // ---- batches -------------------------------------------------------------------------------------------------
-static int batch_setup(mot_handle* h, const int64_t* frame_offsets, int n_frames, size_t* total) {
+// frame_offsets -> device (d_frame_offsets_in when removeStatic will remap them, else d_frame_offsets), optional stamps
+static int batch_setup(mot_handle* h, const int64_t* frame_offsets, int n_frames, size_t* total, bool remap, const float* frame_stamps) {
     if (!h) return MOT_ERR_INVALID;
     if (!frame_offsets || n_frames < 1) return fail(h, MOT_ERR_INVALID, "bad frame_offsets");
     if ((size_t)n_frames > h->frame_capacity) return fail(h, MOT_ERR_CAPACITY, "too many frames in one batch (max 4096)");
     if (frame_offsets[0] != 0) return fail(h, MOT_ERR_INVALID, "frame_offsets[0] must be 0");
-    std::vector<int> fo(n_frames + 1);
+    if (remap && !h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
+    int* fo = h->h_pinned_fo;
     for (int f = 0; f <= n_frames; ++f) {
         if (f && frame_offsets[f] < frame_offsets[f - 1]) return fail(h, MOT_ERR_INVALID, "frame_offsets must be non-decreasing");
         if (frame_offsets[f] > (int64_t)h->max_points) return fail(h, MOT_ERR_CAPACITY, "batch larger than the handle's max_points");
@@ -1254,44 +1305,290 @@ static int batch_setup(mot_handle* h, const int64_t* frame_offsets, int n_frames
     CK(cudaSetDevice(h->device));
     int rc = reset_frame_state(h);
     if (rc != MOT_OK) return rc;
-    CK(cudaMemcpyAsync(h->d_frame_offsets, fo.data(), fo.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(mot_sync(h));  // fo is a stack-owned pageable buffer
-    return MOT_OK;
+    CK(cudaMemcpyAsync(remap ? h->d_frame_offsets_in : h->d_frame_offsets, fo, (size_t)(n_frames + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->have_frame_stamps = frame_stamps != nullptr;
+    if (frame_stamps) {
+        float* fs = reinterpret_cast<float*>(h->h_pinned_fo + h->frame_capacity + 2);
+        std::memcpy(fs, frame_stamps, (size_t)n_frames * sizeof(float));
+        CK(cudaMemcpyAsync(h->d_frame_stamps, fs, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    return MOT_OK;  // the pinned staging is reused only after the next synchronising call on this handle
 }
 
-int mot_cluster_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames) {
+// core of every batch entry: cloud on the device (d_src, total points); removeStatic optional; results stay on the device
+static int batch_core(mot_handle* h, const float4* d_src, size_t total, int n_frames, int do_remove_static, int with_centroids) {
+    int rc;
+    if (do_remove_static && total > 0) {
+        if (d_src == h->d_pts) return fail(h, MOT_ERR_STATE, "internal: removeStatic source aliases its destination");
+        rc = enqueue_remove_static(h, d_src, (int)total, h->d_pts, n_frames);
+        if (rc != MOT_OK) return rc;
+        rc = cluster_core(h, h->d_pts, -1, n_frames, with_centroids != 0, 0.0);
+    } else {
+        rc = cluster_core(h, d_src, (int)total, n_frames, with_centroids != 0, 0.0);
+    }
+    return rc;
+}
+
+int mot_frame_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames, int do_remove_static,
+                           int with_centroids, const float* frame_stamps) {
     size_t total = 0;
-    int rc = batch_setup(h, frame_offsets, n_frames, &total);
+    int rc = batch_setup(h, frame_offsets, n_frames, &total, do_remove_static != 0, frame_stamps);
     if (rc != MOT_OK) return rc;
     if (total > 0 && !d_xyz16) return fail(h, MOT_ERR_INVALID, "null point buffer");
     CK(cudaEventRecord(h->ev[0], h->stream));
-    rc = cluster_core(h, reinterpret_cast<const float4*>(d_xyz16), (int)total, n_frames, false, 0.0);
+    rc = batch_core(h, reinterpret_cast<const float4*>(d_xyz16), total, n_frames, do_remove_static, with_centroids);
+    if (rc != MOT_OK) return rc;
+    return finish_timings(h);
+}
+
+int mot_cluster_batch_device(mot_handle* h, const float* d_xyz16, const int64_t* frame_offsets, int n_frames) {
+    return mot_frame_batch_device(h, d_xyz16, frame_offsets, n_frames, 0, 0, nullptr);
+}
+
+// copies the batch result to caller buffers (host or device pointers)
+static int batch_fetch(mot_handle* h, int n_frames, int32_t* frame_kept_offsets, int32_t* frame_cluster_offsets, int32_t* cluster_offsets,
+                       size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats,
+                       float* centroids_xyzi, size_t table_capacity) {
+    if (n_clusters) *n_clusters = h->res_K;
+    if (n_frames > 1) {
+        if (frame_kept_offsets) CK(cudaMemcpyAsync(frame_kept_offsets, h->d_frame_offsets, (size_t)(n_frames + 1) * 4, cudaMemcpyDefault, h->stream));
+        if (frame_cluster_offsets) CK(cudaMemcpyAsync(frame_cluster_offsets, h->d_frame_cl_offsets, (size_t)(n_frames + 1) * 4, cudaMemcpyDefault, h->stream));
+    } else {
+        const int32_t kept[2] = {0, h->res_M}, cl[2] = {0, h->res_K};
+        if (frame_kept_offsets) CK(cudaMemcpyAsync(frame_kept_offsets, kept, sizeof(kept), cudaMemcpyDefault, h->stream));
+        if (frame_cluster_offsets) CK(cudaMemcpyAsync(frame_cluster_offsets, cl, sizeof(cl), cudaMemcpyDefault, h->stream));
+        CK(mot_sync(h));  // the two arrays live on this stack frame
+    }
+    return fetch_result(h, nullptr, 0, cluster_offsets, offsets_capacity, point_indices, indices_capacity, stats, centroids_xyzi, table_capacity);
+}
+
+int mot_frame_batch(mot_handle* h, const float* xyz, int point_stride_bytes, const int64_t* frame_offsets, int n_frames, int do_remove_static,
+                    const float* frame_stamps, int32_t* frame_kept_offsets, int32_t* frame_cluster_offsets, int32_t* cluster_offsets,
+                    size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats,
+                    float* centroids_xyzi, size_t table_capacity) {
+    if (h && point_stride_bytes != 16 && point_stride_bytes != 12) return fail(h, MOT_ERR_INVALID, "point_stride_bytes must be 16 (pcl::PointXYZ) or 12 (packed xyz)");
+    size_t total = 0;
+    int rc = batch_setup(h, frame_offsets, n_frames, &total, do_remove_static != 0, frame_stamps);
+    if (rc != MOT_OK) return rc;
+    if (total > 0 && !xyz) return fail(h, MOT_ERR_INVALID, "null point buffer");
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev[0], st));
+    // the cloud lands in d_in when removeStatic will compact it into d_pts, else directly in d_pts
+    float4* d_cloud = do_remove_static ? h->d_in : h->d_pts;
+    if (total) {
+        if (point_stride_bytes == 16) {
+            CK(cudaMemcpyAsync(d_cloud, xyz, total * 16, cudaMemcpyHostToDevice, st));
+        } else {  // packed xyz: 25 % fewer PCIe bytes, expanded to the PointXYZ layout on the device (k_pc2_unpack)
+            rc = ensure_raw(h, total * 12);
+            if (rc != MOT_OK) return rc;
+            CK(cudaMemcpyAsync(h->d_raw, xyz, total * 12, cudaMemcpyHostToDevice, st));
+            const Chunking ck = make_chunking((long long)total, 256, RSK_MAX_GRID);
+            LAUNCH(KID_PC2_UNPACK, k_pc2_unpack<<<ck.grid, 256, 0, st>>>(h->d_raw, (int)total, ck.chunk, 12u, 0u, 4u, 8u, 0, d_cloud, h->d_blk));
+        }
+    }
+    rc = batch_core(h, d_cloud, total, n_frames, do_remove_static, centroids_xyzi != nullptr);
+    if (rc != MOT_OK) return rc;
+    rc = batch_fetch(h, n_frames, frame_kept_offsets, frame_cluster_offsets, cluster_offsets, offsets_capacity, point_indices, indices_capacity,
+                     n_clusters, stats, centroids_xyzi, table_capacity);
     if (rc != MOT_OK) return rc;
     return finish_timings(h);
 }
 
 int mot_cluster_batch(mot_handle* h, const float* xyz16, const int64_t* frame_offsets, int n_frames, int32_t* frame_cluster_offsets,
                       int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters) {
-    size_t total = 0;
-    int rc = batch_setup(h, frame_offsets, n_frames, &total);
+    return mot_frame_batch(h, xyz16, 16, frame_offsets, n_frames, 0, nullptr, nullptr, frame_cluster_offsets, cluster_offsets, offsets_capacity,
+                           point_indices, indices_capacity, n_clusters, nullptr, nullptr, 0);
+}
+
+// ---- fused clusterPointCloud (MOT.cpp:444-505): fromROSMsg -> VoxelGrid -> removeStatic -> extract -> getCentroid ----------------
+int mot_cluster_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points, uint32_t point_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                            int is_bigendian, float voxel_leaf_size, int do_remove_static, double stamp_minus_time_init, float* kept_xyz16,
+                            size_t kept_capacity, size_t* m, int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices,
+                            size_t indices_capacity, int32_t* n_clusters, mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity) {
+    int rc = check_frame_args(h, data, n_points);
     if (rc != MOT_OK) return rc;
-    if (total > 0 && !xyz16) return fail(h, MOT_ERR_INVALID, "null point buffer");
-    CK(cudaEventRecord(h->ev[0], h->stream));
-    if (total) CK(cudaMemcpyAsync(h->d_pts, xyz16, total * 16, cudaMemcpyHostToDevice, h->stream));
-    rc = cluster_core(h, h->d_pts, (int)total, n_frames, false, 0.0);
+    if (point_step < 12 || (uint64_t)off_x + 4 > point_step || (uint64_t)off_y + 4 > point_step || (uint64_t)off_z + 4 > point_step)
+        return fail(h, MOT_ERR_INVALID, "bad PointCloud2 layout");
+    if (n_points > SIZE_MAX / point_step) return fail(h, MOT_ERR_INVALID, "PointCloud2 payload size overflows");
+    if (do_remove_static && !h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
+    CK(cudaSetDevice(h->device));
+    rc = reset_frame_state(h);
     if (rc != MOT_OK) return rc;
-    if (n_clusters) *n_clusters = h->res_K;
-    if (frame_cluster_offsets) {
-        if (n_frames > 1) {
-            CK(cudaMemcpyAsync(frame_cluster_offsets, h->d_frame_cl_offsets, (size_t)(n_frames + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
-        } else {
-            frame_cluster_offsets[0] = 0;
-            frame_cluster_offsets[1] = h->res_K;
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev[0], st));
+    int warn = MOT_OK;
+    int n = (int)n_points;
+    const float4* cloud = h->d_pts;
+    if (n > 0) {
+        // fromROSMsg: wire format -> PointXYZ (d_in), then the finite points in input order (d_pts) -- PCL's VoxelGrid / kd-tree
+        // skip non-finite points of a non-dense cloud
+        rc = ensure_raw(h, n_points * (size_t)point_step);
+        if (rc != MOT_OK) return rc;
+        CK(cudaMemcpyAsync(h->d_raw, data, n_points * (size_t)point_step, cudaMemcpyDefault, st));
+        const Chunking ck = make_chunking(n, 256, RSK_MAX_GRID);
+        LAUNCH(KID_PC2_UNPACK, k_pc2_unpack<<<ck.grid, 256, 0, st>>>(h->d_raw, n, ck.chunk, point_step, off_x, off_y, off_z, is_bigendian, h->d_in, h->d_blk));
+        const int tiles = (n + C1P_TILE - 1) / C1P_TILE;
+        CK(cudaMemsetAsync(h->d_c1p_status, 0, ((size_t)tiles + 1) * sizeof(unsigned), st));
+        LAUNCH(KID_PC2_COMPACT, k_compact_onepass<1><<<tiles, C1P_THREADS, 0, st>>>(h->d_in, n, h->mp, nullptr, 0, h->d_pts, h->d_c1p_status, tiles,
+                                                                                 h->d_counts + CNT_M, h->d_bbox, nullptr, 1, nullptr,
+                                                                                 h->d_counts + CNT_FLAGS));
+        CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(mot_sync(h));
+        n = h->h_pinned[8 + CNT_M];
+        if (voxel_leaf_size > 0.0f && n > 0) {  // vg.setLeafSize(L, L, 20 L); vg.filter() (MOT.cpp:452-456); d_pts -> d_pts
+            rc = reset_bbox(h);
+            if (rc != MOT_OK) return rc;
+            int V = 0;
+            rc = voxel_grid_device(h, h->d_pts, n, voxel_leaf_size, voxel_leaf_size, 20.0f * voxel_leaf_size, &V);
+            if (rc < 0) return rc;
+            warn = rc;
+            n = V;
         }
+        rc = reset_bbox(h);
+        if (rc != MOT_OK) return rc;
+        CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), st));
     }
-    rc = fetch_result(h, nullptr, 0, cluster_offsets, offsets_capacity, point_indices, indices_capacity, nullptr, nullptr, 0);
+    if (do_remove_static && n > 0) {  // removeStatic (MOT.cpp:461): d_pts -> d_in
+        rc = enqueue_remove_static(h, h->d_pts, n, h->d_in);
+        if (rc != MOT_OK) return rc;
+        cloud = h->d_in;
+        rc = cluster_core(h, cloud, -1, 1, centroids_xyzi != nullptr, stamp_minus_time_init);
+    } else {
+        rc = cluster_core(h, cloud, n, 1, centroids_xyzi != nullptr, stamp_minus_time_init);
+    }
     if (rc != MOT_OK) return rc;
-    return finish_timings(h);
+    if (m) *m = (size_t)h->res_M;
+    if (n_clusters) *n_clusters = h->res_K;
+    rc = fetch_result(h, kept_xyz16, kept_capacity, cluster_offsets, offsets_capacity, point_indices, indices_capacity, stats, centroids_xyzi,
+                      table_capacity);
+    if (rc != MOT_OK) return rc;
+    rc = finish_timings(h);
+    return rc != MOT_OK ? rc : warn;
+}
+
+// ---- multi-GPU frame batches: one host thread per handle, contiguous frame ranges, tables land in the caller's buffers ----
+namespace {
+__global__ void k_add_offset(int* __restrict__ a, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] += v;
+}
+struct ShardJob {
+    mot_handle* h = nullptr;
+    int f0 = 0, f1 = 0;  // frame range
+    int rc = MOT_OK;
+    int K = 0, total = 0, M = 0;
+    int k_base = 0, idx_base = 0, kept_base = 0;
+};
+}  // namespace
+
+int mot_batch_run(mot_handle* const* handles, int n_handles, const float* xyz, int point_stride_bytes, const int64_t* frame_offsets, int n_frames,
+                  int do_remove_static, const float* frame_stamps, int32_t* frame_kept_offsets, int32_t* frame_cluster_offsets,
+                  int32_t* cluster_offsets, size_t offsets_capacity, int32_t* point_indices, size_t indices_capacity, int32_t* n_clusters,
+                  mot_cluster_stat* stats, float* centroids_xyzi, size_t table_capacity) {
+    if (!handles || n_handles < 1 || !handles[0]) return MOT_ERR_INVALID;
+    mot_handle* h0 = handles[0];
+    if (!frame_offsets || n_frames < 1 || frame_offsets[0] != 0) return fail(h0, MOT_ERR_INVALID, "bad frame_offsets");
+    if (point_stride_bytes != 16 && point_stride_bytes != 12) return fail(h0, MOT_ERR_INVALID, "point_stride_bytes must be 16 or 12");
+    for (int g = 0; g < n_handles; ++g)
+        if (!handles[g]) return fail(h0, MOT_ERR_INVALID, "null handle");
+    std::vector<ShardJob> jobs((size_t)n_handles);
+    for (int g = 0; g < n_handles; ++g) {  // contiguous frame ranges, the rule of shard.frame_range
+        jobs[g].h = handles[g];
+        jobs[g].f0 = (int)((long long)n_frames * g / n_handles);
+        jobs[g].f1 = (int)((long long)n_frames * (g + 1) / n_handles);
+    }
+    const size_t stride_floats = (size_t)point_stride_bytes / 4;
+    // phase 1: every handle runs its frame range, results stay on its device
+    auto phase1 = [&](ShardJob& j) {
+        const int nf = j.f1 - j.f0;
+        if (nf == 0) return;
+        std::vector<int64_t> fo((size_t)nf + 1);
+        for (int f = 0; f <= nf; ++f) fo[f] = frame_offsets[j.f0 + f] - frame_offsets[j.f0];
+        mot_handle* h = j.h;
+        size_t total = 0;
+        j.rc = batch_setup(h, fo.data(), nf, &total, do_remove_static != 0, frame_stamps ? frame_stamps + j.f0 : nullptr);
+        if (j.rc != MOT_OK) return;
+        j.rc = [&]() -> int {
+            cudaStream_t st = h->stream;
+            CK(cudaEventRecord(h->ev[0], st));
+            float4* d_cloud = do_remove_static ? h->d_in : h->d_pts;
+            const float* src = xyz + (size_t)frame_offsets[j.f0] * stride_floats;
+            if (total) {
+                if (point_stride_bytes == 16) {
+                    CK(cudaMemcpyAsync(d_cloud, src, total * 16, cudaMemcpyDefault, st));
+                } else {
+                    int rc = ensure_raw(h, total * 12);
+                    if (rc != MOT_OK) return rc;
+                    CK(cudaMemcpyAsync(h->d_raw, src, total * 12, cudaMemcpyDefault, st));
+                    const Chunking ck = make_chunking((long long)total, 256, RSK_MAX_GRID);
+                    LAUNCH(KID_PC2_UNPACK, k_pc2_unpack<<<ck.grid, 256, 0, st>>>(h->d_raw, (int)total, ck.chunk, 12u, 0u, 4u, 8u, 0, d_cloud, h->d_blk));
+                }
+            }
+            int rc = batch_core(h, d_cloud, total, nf, do_remove_static, centroids_xyzi != nullptr);
+            if (rc != MOT_OK) return rc;
+            rc = finish_timings(h);
+            return rc;
+        }();
+        j.K = h->res_K; j.total = h->res_total; j.M = h->res_M;
+    };
+    // phase 2: shift the shard's offsets by what precedes it and copy its tables into the caller's arrays
+    auto phase2 = [&](ShardJob& j) {
+        const int nf = j.f1 - j.f0;
+        if (nf == 0) return;
+        mot_handle* h = j.h;
+        j.rc = [&]() -> int {
+            CK(cudaSetDevice(h->device));
+            cudaStream_t st = h->stream;
+            const bool last = j.f1 == n_frames;
+            if (j.idx_base) k_add_offset<<<(j.K + 1 + 255) / 256, 256, 0, st>>>(h->d_cl_offsets, j.K + 1, j.idx_base);
+            if (cluster_offsets) CK(cudaMemcpyAsync(cluster_offsets + j.k_base, h->d_cl_offsets, (size_t)(j.K + (last ? 1 : 0)) * 4, cudaMemcpyDefault, st));
+            if (point_indices && j.total) CK(cudaMemcpyAsync(point_indices + j.idx_base, h->d_vals[h->res_idx_buf], (size_t)j.total * 4, cudaMemcpyDefault, st));
+            if (stats && j.K) CK(cudaMemcpyAsync(stats + j.k_base, h->d_stats, (size_t)j.K * sizeof(ClusterStat), cudaMemcpyDefault, st));
+            if (centroids_xyzi && j.K) CK(cudaMemcpyAsync(centroids_xyzi + 4 * (size_t)j.k_base, h->d_centroids, (size_t)j.K * 16, cudaMemcpyDefault, st));
+            if (nf > 1) {
+                if (frame_cluster_offsets) {
+                    if (j.k_base) k_add_offset<<<(nf + 1 + 255) / 256, 256, 0, st>>>(h->d_frame_cl_offsets, nf + 1, j.k_base);
+                    CK(cudaMemcpyAsync(frame_cluster_offsets + j.f0, h->d_frame_cl_offsets, (size_t)(nf + (last ? 1 : 0)) * 4, cudaMemcpyDefault, st));
+                }
+                if (frame_kept_offsets) {
+                    if (j.kept_base) k_add_offset<<<(nf + 1 + 255) / 256, 256, 0, st>>>(h->d_frame_offsets, nf + 1, j.kept_base);
+                    CK(cudaMemcpyAsync(frame_kept_offsets + j.f0, h->d_frame_offsets, (size_t)(nf + (last ? 1 : 0)) * 4, cudaMemcpyDefault, st));
+                }
+            } else {  // a single frame has no per-frame tables on the device
+                const int32_t cl[2] = {j.k_base, j.k_base + j.K}, kept[2] = {j.kept_base, j.kept_base + j.M};
+                if (frame_cluster_offsets) CK(cudaMemcpyAsync(frame_cluster_offsets + j.f0, cl, (last ? 2 : 1) * 4, cudaMemcpyDefault, st));
+                if (frame_kept_offsets) CK(cudaMemcpyAsync(frame_kept_offsets + j.f0, kept, (last ? 2 : 1) * 4, cudaMemcpyDefault, st));
+                CK(mot_sync(h));
+            }
+            CK(cudaGetLastError());
+            CK(mot_sync(h));
+            h->have_result = false;  // the shard's tables were shifted in place: they now belong to the merged result
+            return MOT_OK;
+        }();
+    };
+    auto run_all = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n_handles; ++g) th.emplace_back([&, g] { fn(jobs[g]); });
+        fn(jobs[0]);
+        for (auto& t : th) t.join();
+    };
+    run_all(phase1);
+    for (auto& j : jobs)
+        if (j.rc != MOT_OK) { if (j.h != h0) h0->err = j.h->err; return j.rc; }
+    long long k_sum = 0, idx_sum = 0, kept_sum = 0;
+    for (auto& j : jobs) {
+        j.k_base = (int)k_sum; j.idx_base = (int)idx_sum; j.kept_base = (int)kept_sum;
+        k_sum += j.K; idx_sum += j.total; kept_sum += j.M;
+    }
+    if (n_clusters) *n_clusters = (int32_t)k_sum;
+    if (idx_sum > 0x7fffffffll || kept_sum > 0x7fffffffll) return fail(h0, MOT_ERR_CAPACITY, "batch result does not fit 32-bit offsets");
+    if (cluster_offsets && offsets_capacity < (size_t)k_sum + 1) return fail(h0, MOT_ERR_CAPACITY, "cluster_offsets buffer too small");
+    if (point_indices && indices_capacity < (size_t)idx_sum) return fail(h0, MOT_ERR_CAPACITY, "point_indices buffer too small");
+    if ((stats || centroids_xyzi) && table_capacity < (size_t)k_sum) return fail(h0, MOT_ERR_CAPACITY, "table buffers too small");
+    run_all(phase2);
+    for (auto& j : jobs)
+        if (j.rc != MOT_OK) { if (j.h != h0) h0->err = j.h->err; return j.rc; }
+    return MOT_OK;
 }
 
 // ---- IHGP ----------------------------------------------------------------------------------------------------

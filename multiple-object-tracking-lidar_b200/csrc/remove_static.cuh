@@ -169,6 +169,135 @@ __global__ void __launch_bounds__(RSK_THREADS) k_rs_compact(const float4* __rest
     }
 }
 
+// ---- single-pass stable compaction (decoupled look-back) ---------------------------------------------------------------------
+// k_rs_count + k_rs_compact read the cloud twice (32 N + 16 M bytes).  k_compact_onepass reads it once (16 N + 16 M): a CTA takes
+// the next tile (ticket: every predecessor tile is running or done), decides its points, publishes the tile's kept count in
+// one 32-bit status word (2 flag bits + 30 value bits, so no fence is needed), obtains its exclusive prefix by walking back
+// over the predecessors' words 32 at a time, and writes its kept points in input order (MOT.cpp:694 appends in input order).
+// The same pass accumulates the bounding box / non-finite flag of the kept points (the voxel grid needs them) and, for a
+// batch of frames, the frame boundaries of the compacted cloud.
+// MODE 0: keep = removeStatic's map lookup (MOT.cpp:664-706); MODE 1: keep = all three coordinates finite
+// (pcl::removeNaNFromPointCloud, used behind fromROSMsg).
+constexpr int C1P_THREADS = 256;
+constexpr int C1P_ITEMS = 8;
+constexpr int C1P_TILE = C1P_THREADS * C1P_ITEMS;
+constexpr unsigned C1P_AGG = 1u << 30, C1P_INCL = 2u << 30, C1P_VALUE = (1u << 30) - 1u;
+constexpr int C1P_SPIN_LIMIT = 1 << 24;  // a stuck look-back raises flag 2 instead of hanging the GPU
+
+template <int MODE>
+__global__ void __launch_bounds__(C1P_THREADS) k_compact_onepass(const float4* __restrict__ pts, int n, MapParams mp, const uint32_t* __restrict__ gbits,
+                                                                  int use_smem, float4* __restrict__ out, unsigned* status /* [tiles] + ticket */,
+                                                                  int n_tiles, int* __restrict__ total_out, int* __restrict__ bbox,
+                                                                  const int* __restrict__ frame_off_in, int n_frames, int* __restrict__ frame_off_out,
+                                                                  int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) uint32_t rs_sbits[];
+    __shared__ uint64_t bar;
+    __shared__ int scratch[36];
+    __shared__ int s_tile, s_base;
+    __shared__ int sbox[6];
+    const uint32_t* bits = MODE == 0 ? rs_stage_bitmap(gbits, mp.n_words, use_smem != 0, rs_sbits, &bar) : nullptr;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(status + n_tiles, 1u);
+    if (threadIdx.x < 3) sbox[threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) sbox[threadIdx.x] = (int)0x80000000;
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) return;
+    const int tile_begin = tile * C1P_TILE;
+    // blocked arrangement: a thread owns C1P_ITEMS consecutive points (one 128-byte line), so ranks are input order
+    const int i0 = tile_begin + threadIdx.x * C1P_ITEMS;
+    float4 p[C1P_ITEMS];
+    unsigned keepm = 0;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < C1P_ITEMS; ++k)
+        if (i0 + k < n) p[k] = ld_stream(pts + i0 + k);
+#pragma unroll
+    for (int k = 0; k < C1P_ITEMS; ++k) {
+        if (i0 + k >= n) break;
+        const bool fin = (fabsf(p[k].x) < INFINITY) && (fabsf(p[k].y) < INFINITY) && (fabsf(p[k].z) < INFINITY);
+        const bool keep = MODE == 0 ? rs_keep(p[k], mp, bits) : fin;
+        if (keep) {
+            keepm |= 1u << k;
+            bad |= !fin;
+            mn[0] = fminf(mn[0], p[k].x); mn[1] = fminf(mn[1], p[k].y); mn[2] = fminf(mn[2], p[k].z);
+            mx[0] = fmaxf(mx[0], p[k].x); mx[1] = fmaxf(mx[1], p[k].y); mx[2] = fmaxf(mx[2], p[k].z);
+        }
+    }
+    int tile_total;
+    const int excl = block_exclusive_scan(__popc(keepm), scratch, &tile_total);
+    // publish, then look back (warp 0)
+    if (threadIdx.x == 0) __stcg(status + tile, (tile == 0 ? C1P_INCL : C1P_AGG) | (unsigned)tile_total);
+    if (warp_id() == 0) {
+        int prefix = 0;
+        const int lane = lane_id();
+        int t = tile - 1, spins = 0;
+        while (t >= 0) {
+            const int mine = t - lane;
+            const unsigned sv = mine >= 0 ? __ldcg(status + mine) : C1P_INCL;  // before tile 0: an inclusive prefix of 0
+            const unsigned f = sv >> 30;
+            const unsigned incl_m = __ballot_sync(kFull, f == 2u), empty_m = __ballot_sync(kFull, f == 0u);
+            const int first_incl = incl_m ? __ffs(incl_m) - 1 : 32;                 // nearest predecessor holding an inclusive prefix
+            const unsigned need = first_incl >= 31 ? 0xffffffffu : ((2u << first_incl) - 1u);  // lanes 0 .. first_incl
+            if (empty_m & need) {
+                if (++spins > C1P_SPIN_LIMIT) { if (lane == 0) atomicOr(err_flag, 2); break; }
+                continue;
+            }
+            int v = (need >> lane) & 1u ? (int)(sv & C1P_VALUE) : 0;
+            v = warp_sum(v);
+            prefix += v;
+            if (incl_m) break;
+            t -= 32;
+        }
+        if (lane == 0) {
+            s_base = prefix;
+            __stcg(status + tile, C1P_INCL | (unsigned)(prefix + tile_total));
+            if (tile == n_tiles - 1) *total_out = prefix + tile_total;
+        }
+    }
+    // bbox of the kept points while the look-back runs
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(kFull, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(kFull, mx[d], o));
+        }
+    if (lane_id() == 0 && tile_total > 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&sbox[d], float_to_ordered(mn[d]));
+            atomicMax(&sbox[3 + d], float_to_ordered(mx[d]));
+        }
+    }
+    if (__any_sync(kFull, bad) && lane_id() == 0) atomicOr(&bbox[6], 1);
+    __syncthreads();
+    const int base = s_base;
+    if (threadIdx.x < 6 && tile_total > 0) {
+        if (threadIdx.x < 3) atomicMin(&bbox[threadIdx.x], sbox[threadIdx.x]);
+        else atomicMax(&bbox[threadIdx.x], sbox[threadIdx.x]);
+    }
+    int w = base + excl;
+#pragma unroll
+    for (int k = 0; k < C1P_ITEMS; ++k)
+        if ((keepm >> k) & 1u) st_stream(out + w++, p[k]);
+    // frame boundaries of the compacted cloud: boundary b (an input index) moves to the output position point b gets / would get
+    if (frame_off_out) {
+        const int tile_end = min(n, tile_begin + C1P_TILE);
+        int lo = 0, hi = n_frames + 1;  // first f with frame_off_in[f] >= tile_begin
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (frame_off_in[mid] < tile_begin) lo = mid + 1; else hi = mid;
+        }
+        for (int f = lo; f <= n_frames; ++f) {
+            const int b = frame_off_in[f];
+            if (b >= tile_end && !(b == n && tile == n_tiles - 1)) break;
+            if (b == n) { if (threadIdx.x == 0) frame_off_out[f] = base + tile_total; continue; }
+            if (b >= i0 && b < i0 + C1P_ITEMS) frame_off_out[f] = base + excl + __popc(keepm & ((1u << (b - i0)) - 1u));
+        }
+    }
+}
+
 // Bounding box + finiteness of an already compacted cloud (mot_cluster without removeStatic).  Two points per
 // thread and iteration in flight, block-level reduction in shared memory, six global atomics per block.
 __global__ void __launch_bounds__(256) k_bbox(const float4* __restrict__ pts, int n, int* __restrict__ bbox) {
