@@ -10,10 +10,14 @@ size filter + CSR emission, per-cluster table) over a batch of `--frames` DISTIN
 other; with the default 8 frames the step's inputs are 128 MiB > the 126 MB L2, so no frame is served from a
 warm L2.  N > 1: every rank clusters its own frames (weak scaling) and rank 0 gathers the cluster tables.
 
-value  = points/s with the frames already resident in HBM (mot_frame_device; CUDA events on the handle's stream).
-e2e    = the same metric through the reference-facing call mot_cluster() with pinned HOST buffers: H2D copy of
-         the cloud and D2H copy of the CSR result inside the timed region.
-The CPU oracle (oracle/) is only used for the cpu_baseline leg and for --impl reference.
+value  = points/s with the frames already resident in HBM (mot_cluster_batch_device; CUDA events on the handle's stream);
+         the median of --reps timed regions of exactly --steps steps each (all regions are listed in `timed_regions_ms`).
+e2e    = the same metric through the reference-facing call mot_cluster_batch() with pinned HOST buffers: H2D copy of
+         the cloud and D2H copy of the CSR result inside the timed region; `h2d_ceiling` is the pinned-copy bandwidth of
+         all ranks copying at once on this box, `frac_of_ceiling` says how much of it the call reaches.
+configs = the other BASELINE configs (c1, c3, c4, c5) at full size on rank 0, each with its parity against the oracle
+         checked in the same run (N = 1 only; --no-configs skips it).
+The CPU oracle (oracle/) is only used for the parity checks, the cpu_baseline leg and for --impl reference.
 """
 import argparse
 import json
@@ -30,6 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
+# what one step of `--impl reference` clusters (a full step of the GPU arm would take the CPU path > 10 minutes per step)
+REFERENCE_SAMPLE = ("--impl reference clusters one 1/16 azimuth wedge (~65k points) of a c2 frame per host thread and step; "
+                    "once per run it also times one full 2^20-point frame on one thread (reported as full_frame)")
 METRIC = "euclidean_clustering_throughput"
 UNIT = "Mpoints/s"
 
@@ -39,7 +46,8 @@ def make_config(p, n_pts, F, world):
     return {"workload": "c2", "points_per_frame": n_pts, "frames_per_step_per_gpu": F, "cluster_tolerance": p["cluster_tolerance"],
             "min_cluster_size": p["min_cluster_size"], "max_cluster_size": p["max_cluster_size"],
             "l2_policy": f"{F} distinct frames per step ({F * n_pts * 16 >> 20} MiB of input > 126 MB L2)",
-            "parallelism": f"frames sharded over {world} GPU(s), tables gathered to rank 0" if world > 1 else "single GPU"}
+            "parallelism": f"frames sharded over {world} GPU(s), tables gathered to rank 0" if world > 1 else "single GPU",
+            "reference_sample": REFERENCE_SAMPLE}
 
 
 def peaks():
@@ -107,6 +115,12 @@ def kernel_bytes(name, M, cf, cc, K, total, key_bytes, n_sort_passes, R_G=1024 *
         "k_coarse_records": 12 * cf + 80 * cc,            # record (16 B) + neighbour row (64 B) per coarse cell
         "k_uf_sparse": 16 * M + 80 * cc + 8 * cf,         # every sorted point once + record/neighbour row + parent r/w
         "k_uf_sparse2": 16 * M + 80 * cc + 8 * cf,        # same traffic, half a warp per coarse cell
+        "k_cell_local": 16 * M + 41 * cf + 56 * cc,         # every sorted point once; cell tables in, boxes / records / parents out
+        "k_uf_fused": 36 * cc + 40 * cf,                    # keys, records, hash, boxes, parents (points only for ambiguous pairs)
+        "k_uf_cross": 68 * cc + 40 * cf,
+        "k_uf_survivors": 36 * cc,
+        "k_uf_walk": 40 * cf,
+        "k_compact_onepass<map>": 32 * M,                   # overwritten by the caller with 16 N + 16 M where N is known
         "k_uf_flatten<in-place>": 8 * cf,
         "k_uf_flatten<root>": 8 * cf,
         "k_comp_accumulate": 16 * cf,
@@ -230,17 +244,25 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_wall0 = time.perf_counter()
-    trk.timer_start()
-    launches = run_steps(lambda s, i: step_device(gather, s, i), args.steps, gather)
-    ms = trk.timer_stop()
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    if dist:
-        dist.barrier()
-    t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
+    regions = []
+    launches = 0
+    for rep in range(max(1, args.reps)):  # every region: exactly --steps steps between a barrier + synchronize on both sides
+        trk.timer_start()
+        n_l = run_steps(lambda s, i: step_device(gather, s, i), args.steps, gather)
+        ms = trk.timer_stop()
+        torch.cuda.synchronize()
+        if rep == 0:
+            launches = n_l
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        regions.append(float(t[0]))
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3 / max(1, args.reps)
+    t = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, wall_max = float(t[0]), float(t[1])
+    ms_max, wall_max = float(np.median(regions)), float(t[0])
     pts_per_step = world * F * n_pts
     value = pts_per_step * args.steps / (ms_max * 1e-3) / 1e6
 
@@ -271,6 +293,27 @@ def run_b200(args, rank, world, local_rank):
         dist.barrier()
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = pts_per_step * e2e_steps / (float(te[0]) * 1e-3) / 1e6
+
+    # ---- what the box can copy: every rank copies its pinned step input to its GPU at the same time (same bytes as a step) ----
+    d_sink = torch.empty_like(d_all)
+    for _ in range(2):
+        d_sink.copy_(h_all, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(4):
+        d_sink.copy_(h_all, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    tc = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.barrier()
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_gbs_per_gpu = 4 * F * n_pts * 16 / (float(tc[0]) * 1e-3) / 1e9
+    h2d_ceiling = world * h2d_gbs_per_gpu * 1e9 / 16 / 1e6  # Mpoints/s if the step were nothing but its input copy
+    del d_sink
 
     # ---- the same frames through the per-frame call the reference's callback would make (mot_cluster, one frame per
     # call, pinned host buffers, H2D + D2H inside the timed region), frames dealt round-robin to the S handles ----
@@ -355,7 +398,8 @@ def run_b200(args, rank, world, local_rank):
     # north_star's sub-target: grid build + union-find against (104 + 16 P) M + 16 C bytes
     k15 = ("k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count", "k_hash_clear", "k_cells_write",
            "k_coarse_records", "k_uf_sparse", "k_uf_sparse2", "k_uf_dense<1>", "k_uf_dense<2>", "k_uf_flatten<in-place>", "k_uf_flatten<root>",
-           "k_uf_pairs<1>", "k_uf_pairs<2>")
+           "k_uf_pairs<1>", "k_uf_pairs<2>", "k_cell_local", "k_uf_fused", "k_uf_cross", "k_uf_survivors", "k_uf_walk", "k_uf_heavy<1>",
+           "k_uf_heavy<2>", "k_uf_flatten_if")
     t15_us = sum(v[0] for kname, v in prof.items() if kname in k15) / prof_steps * 1e3
     b15 = (104 + 16 * P) * M + 16 * grid["coarse_cells"]
     grid_uf = {"alg_bytes_per_step": b15, "kernel_us_per_step": round(t15_us, 1), "gbs": round(b15 / (t15_us * 1e-6) / 1e9, 1),
@@ -363,11 +407,14 @@ def run_b200(args, rank, world, local_rank):
 
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": round(ms_max / args.steps, 4), "timed_regions_ms": [round(r, 3) for r in regions], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": make_config(p, n_pts, F, world),
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": F * n_pts * 16, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                 "api": "mot_cluster_batch (host pinned buffers in, CSR out)",
+                "h2d_ceiling": {"value": round(h2d_ceiling, 1), "unit": UNIT, "gbs_per_gpu": round(h2d_gbs_per_gpu, 2),
+                                "how": "all ranks copy their pinned step input to their GPU at once (cudaMemcpyAsync, CUDA events, max over ranks)"},
+                "frac_of_ceiling": round(e2e_value / h2d_ceiling, 3),
                 "per_frame_api": {"value": round(e2e_per_frame, 2), "unit": UNIT, "api": "mot_cluster, one frame per call"}},
         "single_frame_latency_us": round(single_frame_us, 1),
         "streams_per_gpu": S, "host_wait": os.environ.get("MOT_SYNC", "spin"),
@@ -376,10 +423,13 @@ def run_b200(args, rank, world, local_rank):
         "roofline": roofline,
         "frame_roofline": whole,
         "grid_build_union_find_roofline": grid_uf,
-        "kernels": kernels[:14],
+        "kernels": kernels[:16],
         "wall_ms_per_step": round(wall_max / args.steps, 4),
         "result": {"kept_points": M, "clusters": K, "indices": total, **grid},
     }
+    if rank == 0 and world == 1 and not args.no_configs:
+        import bench_configs
+        out["configs"] = bench_configs.run(mot, entry.load_oracle(), local_rank, peak, quick=args.quick_configs)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(frames_np[0], p)
     for t_ in trks:
@@ -423,7 +473,7 @@ def run_reference(args, rank, world):
     p = synth.C2_PARAMS
     scene = synth.scene_c2()
     cores = os.cpu_count() or 1
-    threads = min(cores, 64)
+    threads = max(1, min(cores, 64) - 1)  # one core is left to the full-frame timing that runs beside the steps
     base = [wedge(scene.frame(f), 1.0 / 16) for f in range(min(threads, 8))]
     work = [base[i % len(base)] for i in range(threads)]
     pts = sum(len(w) for w in work)
@@ -431,24 +481,42 @@ def run_reference(args, rank, world):
     def one(w):
         return oracle.cluster_kdtree(w, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"], build_twice=True)
 
+    # the step's real unit, once: a whole 2^20-point frame on one thread (the reference's callback is single threaded,
+    # MOT.cpp:117-121).  The per-core cost grows faster than the point count, so the wedge figure flatters the CPU.
+    full = {}
+
+    def full_frame():
+        fr = scene.frame(0)
+        t0 = time.perf_counter()
+        off, _ = one(fr)
+        dt = time.perf_counter() - t0
+        full.update({"points": len(fr), "seconds": round(dt, 2), "clusters": len(off) - 1, "value_per_core": round(len(fr) / dt / 1e6, 5), "unit": UNIT})
+
+    th_full = threading.Thread(target=full_frame)
+    if not args.no_full_frame:
+        th_full.start()
+
     def step():
         with ThreadPoolExecutor(threads) as ex:
             list(ex.map(one, work))
 
-    for _ in range(min(args.warmup, 1)):
+    warmup = max(args.warmup, 3)  # same rule as the GPU arm
+    for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
+    if not args.no_full_frame:
+        th_full.join()
     value = pts * args.steps / dt / 1e6
-    sample = f"{threads} x 1/16 azimuth wedges of c2 frames ({pts} points per step), one wedge per host thread"
+    sample = f"{threads} x 1/16 azimuth wedges of c2 frames ({pts} points per step), one wedge per host thread; oracle KD-tree + BFS restatement of PCL"
     return {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": make_config(p, 1 << 20, args.frames, world),
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "full_frame": full or None},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -463,6 +531,10 @@ def main():
     ap.add_argument("--streams", type=int, default=6, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-frame", action="store_true", help="reference arm: skip the one-off full-frame timing (~90 s)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c3 / c4 / c5 block (N = 1 only)")
+    ap.add_argument("--quick-configs", action="store_true", help="smaller c3 / c4 shapes in the configs block (smoke runs)")
+    ap.add_argument("--reps", type=int, default=3, help="timed regions of --steps steps each; value is their median")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -15,7 +15,7 @@ def _run(args, timeout=600):
 
 
 def test_reference_arm_json_line():
-    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--no-full-frame"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -23,6 +23,7 @@ def test_reference_arm_json_line():
     assert d["impl"] == "reference" and d["metric"] == "euclidean_clustering_throughput" and d["unit"] == "Mpoints/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["config"]["workload"] == "c2" and "model" not in d["config"]
+    assert "wedge" in d["config"]["reference_sample"] and d["warmup"] == 3  # the sample is stated; warm-up rule of the GPU arm
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 0 and d["gpu_launches"] == 0
@@ -30,7 +31,7 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_only_rank0_prints():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--no-full-frame"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
 
