@@ -119,14 +119,18 @@ struct mot_handle {
     int* d_dense_list = nullptr;
     int* d_nbr = nullptr;
     int dense_cap = 0;
-    int uf_mode = 2;   // 2: cell boxes + local components + thread per (cell, neighbour row) (cell_uf.cuh, default);
+    int uf_mode = 3;   // MOT_UF_MODE 3 (default): 2 for calls with at least uf_auto_points points, else 1 -- the cell path is throughput
+                       // oriented (latency-bound kernels that need ~10^5 coarse cells in flight), the sweep has the shorter critical path;
+                       // 2: cell boxes + local components + fused lookup / root skip / walk (cell_uf.cuh);
                        // 1: coarse-cell warps + TMA staging + brute-force sweep; 0: v1 two-phase fine-cell warps
+    int uf_auto_points = 3 << 19;  // MOT_UF_AUTO: crossover of the two paths (1.5 M points)
+    int uf_mode_now = 2;           // what the current call uses
     void* d_ckey = nullptr;      // sorted coarse keys (u32 or u64)
     unsigned char* d_fcode = nullptr;  // child code (0..7) of every fine cell
     float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
     int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
     int heavy_cap = 0;
-    int uf_light = 64;      // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
+    int uf_light = 256;     // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
     int uf_cross_blocks = 4;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
     int uf_split = 0;        // MOT_UF_SPLIT=1: face rows and the remaining rows as two launches
     int uf_xmode = 2;        // MOT_UF_XMODE 2: k_uf_fused (default); 1: k_uf_survivors + k_uf_walk per phase; 0: k_uf_cross
@@ -312,6 +316,7 @@ template <typename KT>
 int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCodec& g, int total_bits, int n_frames) {
     cudaStream_t st = h->stream;
     KT* keys[2] = {reinterpret_cast<KT*>(h->d_keys[0]), reinterpret_cast<KT*>(h->d_keys[1])};
+    h->uf_mode_now = h->uf_mode == 3 ? (M >= h->uf_auto_points ? 2 : 1) : h->uf_mode;
     LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]));
     const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, h->prof, KID_SORT_HIST);
     const KT* skeys = keys[sb];
@@ -333,7 +338,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
                                                                                reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                               h->d_counts, h->uf_mode == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr, h->uf_mode == 2 ? h->d_fcode : nullptr));
+                                                                               h->d_counts, h->uf_mode_now == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr, h->uf_mode_now == 2 ? h->d_fcode : nullptr));
     CK(cudaEventRecord(h->ev[2], st));
 
     const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
@@ -341,7 +346,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (uf_grid > h->num_sms * 8) uf_grid = h->num_sms * 8;
     int flat_grid = (M + 255) / 256;
     if (flat_grid > h->num_sms * 8) flat_grid = h->num_sms * 8;
-    if (h->uf_mode == 2) {
+    if (h->uf_mode_now == 2) {
         const cudaStream_t main_st = st;
         const bool side = h->uf_stream && !h->prof.on;
         if (side) {
@@ -395,7 +400,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             st = main_st;
             CK(cudaStreamWaitEvent(st, h->ev_uf[1], 0));
         }
-    } else if (h->uf_mode == 1) {
+    } else if (h->uf_mode_now == 1) {
         int rgrid = (M + 15) / 16;
         if (rgrid > h->num_sms * 32) rgrid = h->num_sms * 32;
         LAUNCH(KID_COARSE_REC, k_coarse_records<KT><<<rgrid, 256, 0, st>>>(skeys, h->d_fc_start, h->d_cc_first, h->d_counts,
@@ -751,6 +756,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->heavy_cap = (int)(n / 2 + 4096);
         CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
         CK(dalloc(&h->d_heavy2, (size_t)h->heavy_cap));
+        if (const char* e = getenv("MOT_UF_AUTO")) h->uf_auto_points = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
         if (const char* e = getenv("MOT_UF_XBLOCKS")) h->uf_cross_blocks = std::min(32, std::max(1, atoi(e)));
         if (const char* e = getenv("MOT_UF_SPLIT")) h->uf_split = atoi(e) != 0;

@@ -13,9 +13,20 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def trk(mot):
-    t = mot.Tracker(device=0, max_points=1 << 21, max_tracks=2048)
+@pytest.fixture(scope="module", params=["cell-path", "auto"])
+def trk(mot, request):
+    # every test that takes `trk` runs twice: with the cell-based union-find of round 2 forced (MOT_UF_MODE=2; by default it
+    # only serves calls of >= 1.5 M points) and with the default choice (the round-1 sweep kernels at these sizes)
+    saved = os.environ.get("MOT_UF_MODE")
+    if request.param == "cell-path":
+        os.environ["MOT_UF_MODE"] = "2"
+    try:
+        t = mot.Tracker(device=0, max_points=1 << 21, max_tracks=2048)   # the switch is read by mot_create
+    finally:
+        if saved is None:
+            os.environ.pop("MOT_UF_MODE", None)
+        else:
+            os.environ["MOT_UF_MODE"] = saved
     yield t
     t.close()
 
@@ -218,8 +229,9 @@ def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
     assert not errors, errors
 
 
-ALTERNATIVES = [{"MOT_UF_MODE": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_LIGHT": "1"}, {"MOT_UF_LIGHT": "1024"},
-                {"MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"},
+ALTERNATIVES = [{"MOT_UF_MODE": "2"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0"},
+                {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1", "MOT_UF_PHASES": "7,24"}, {"MOT_UF_MODE": "2", "MOT_UF_FBLOCKS": "2"}, {"MOT_UF_MODE": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1024"},
+                {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0", "MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"},
                 {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}]
 
 
@@ -487,8 +499,9 @@ def test_tracks_table_full_is_not_fatal(mot, oracle):
         assert np.array_equal(out["ids"][:5], r_ids) and (out["ids"][5:] == -1).all()
         np.testing.assert_allclose(out["pos_vel"][:5], r_pv, rtol=RTOL, atol=1e-6)   # matched tracks were filtered as usual
         assert not out["pos_vel"][5:].any()
-    # the old objects disappear; after the purge period (5 s at 10 Hz = 51 callbacks) their slots are free again
-    for f in range(4, 4 + 60):
+    # the old objects disappear.  The purge runs every 51st callback and drops tracks unseen for more than 5 s: the first one
+    # (t = 5.1 s) still finds them 4.8 s old, the second one (t = 10.2 s) frees their slots and the two newcomers register
+    for f in range(4, 4 + 110):
         now = 0.1 * f
         out = t.tracks_step(cen(2, now, x0=100.0), now, thr, freq)
     assert t.last_warning == 0 and out["n_tracks"] <= 3 and (out["ids"] >= 0).all()
