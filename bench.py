@@ -160,7 +160,9 @@ def run_b200(args, rank, world, local_rank):
     all_np = np.ascontiguousarray(np.concatenate(frames_np))
     frame_offsets = np.arange(F + 1, dtype=np.int64) * n_pts
     d_all = torch.from_numpy(all_np).to(dev)          # the step's frames, resident in HBM
-    S = max(1, args.streams)
+    # handles per GPU: 4 saturate the GPU (2: -8 %, 3: -2.4 %, 6: +0.1 %, 8: -1 %; profiles/r02_streams.txt); 3 when the ranks of this node
+    # would otherwise run more host threads (handles + the gather thread) than there are cores
+    S = args.streams if args.streams > 0 else (4 if world * 5 <= (os.cpu_count() or 32) else 3)
     # every handle has a host thread that waits on its stream.  Spinning (the default) is fastest while each thread has a
     # core; when the ranks of this node together run more threads than cores, the waits poll-and-yield instead
     # (MOT_SYNC=yield, read by mot_create): 37.2 vs 34.4 Gpoints/s at 8 GPUs on 32 cores against spinning with 3 streams
@@ -528,7 +530,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16, help="distinct frames per step per GPU")
-    ap.add_argument("--streams", type=int, default=6, help="handles (host thread + CUDA stream each) per GPU working on alternate steps")
+    ap.add_argument("--streams", type=int, default=0, help="handles (host thread + CUDA stream each) per GPU working on alternate steps; 0 = choose")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-frame", action="store_true", help="reference arm: skip the one-off full-frame timing (~90 s)")

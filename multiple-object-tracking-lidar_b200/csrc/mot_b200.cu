@@ -52,7 +52,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -60,7 +60,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass"};
 
 struct mot_handle {
     int device = 0;
@@ -108,6 +108,8 @@ struct mot_handle {
     int* d_frame_offsets_in = nullptr;  // ... of the input cloud, before removeStatic
     unsigned* d_c1p_status = nullptr;  // one-pass compaction: tile status words + ticket
     size_t c1p_tiles = 0;
+    int keys_hist_fused = 0;  // MOT_KEYS_HIST=1: k_cell_keys_hist instead of k_cell_keys + the first k_rs_hist (measured neutral: 107 + 2x35 vs 81 + 3x32 us)
+    int csr_compact = 0;      // MOT_CSR_COMPACT=1: drop the points of filtered-out components before the CSR sort (measured neutral on c2: the compaction pass costs what the smaller sort saves)
     int rs_mode = 1;  // 1: single-pass compaction (decoupled look-back); 0: count + compact (MOT_RS_MODE)
     float* d_frame_stamps = nullptr;  // per-frame centroid intensity (batch mode)
     bool have_frame_stamps = false;
@@ -317,8 +319,16 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     cudaStream_t st = h->stream;
     KT* keys[2] = {reinterpret_cast<KT*>(h->d_keys[0]), reinterpret_cast<KT*>(h->d_keys[1])};
     h->uf_mode_now = h->uf_mode == 3 ? (M >= h->uf_auto_points ? 2 : 1) : h->uf_mode;
-    LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]));
+    if (h->keys_hist_fused && h->rws.mode == 0) {
+        const RsPlan pl = rs_plan(M, total_bits, h->rws);
+        LAUNCH(KID_KEYS, k_cell_keys_hist<KT><<<pl.ck.grid, RS_THREADS, ((size_t)1 << pl.bits0) * sizeof(unsigned), st>>>(cloud, M, pl.ck.chunk, g, h->d_frame_offsets,
+                                                                                                                       keys[0], pl.bits0, h->rws.hist));
+        h->rws.first_hist_done = true;
+    } else {
+        LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]));
+    }
     const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, h->prof, KID_SORT_HIST);
+    h->rws.first_hist_done = false;
     const KT* skeys = keys[sb];
     const uint32_t* svals = h->d_vals[sb];
     h->sorted_buf = sb;
@@ -559,7 +569,23 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     uint32_t* pk[2] = {reinterpret_cast<uint32_t*>(h->d_keys[0]), reinterpret_cast<uint32_t*>(h->d_keys[1])};
     LAUNCH(KID_POINT_RANK, k_point_rank<<<(M + 255) / 256, 256, 0, st>>>(h->d_spts, h->d_vals[h->sorted_buf], h->d_root, h->d_crank, h->d_cmin, M, K, pk[0],
                                                                         h->d_labels));
-    h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, h->prof, KID_PART_HIST);
+    if (h->csr_compact && total < M) {
+        // only the points of kept clusters enter the sort: (rank, index) pairs in index order, then a stable sort by rank
+        uint32_t* ck[2] = {pk[1], pk[0]};
+        uint32_t* cv[2] = {h->d_vals[1], h->d_vals[0]};
+        if (total > 0) {
+            const int tiles = (M + C1P_TILE - 1) / C1P_TILE;
+            CK(cudaMemsetAsync(h->d_c1p_status, 0, ((size_t)tiles + 1) * sizeof(unsigned), st));
+            LAUNCH(KID_CSR_COMPACT, k_compact_keys_onepass<<<tiles, C1P_THREADS, 0, st>>>(pk[0], M, (uint32_t)K, ck[0], cv[0], h->d_c1p_status, tiles,
+                                                                                        h->d_counts + CNT_FLAGS));
+            const int cb = radix_sort_pairs<uint32_t>(st, ck, cv, total, ceil_log2((long long)K + 1), false, h->rws, h->prof, KID_PART_HIST);
+            h->res_idx_buf = cb == 0 ? 1 : 0;
+        } else {
+            h->res_idx_buf = 1;
+        }
+    } else {
+        h->res_idx_buf = radix_sort_pairs<uint32_t>(st, pk, h->d_vals, M, ceil_log2((long long)K + 1), true, h->rws, h->prof, KID_PART_HIST);
+    }
     CK(cudaEventRecord(h->ev[4], st));
 
     // ---- K7 / K8 (on global point indices; batch indices are made frame-local afterwards) ----
@@ -802,6 +828,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->rws.status, h->rws.status_words));
         h->rws.err_flag = h->d_counts + CNT_FLAGS;
         if (const char* e = getenv("MOT_SORT_MODE")) h->rws.mode = atoi(e);
+        if (const char* e = getenv("MOT_SORT_BIGTILE")) h->rws.big_tile_from = atoi(e);
+        if (const char* e = getenv("MOT_KEYS_HIST")) h->keys_hist_fused = atoi(e);
+        if (const char* e = getenv("MOT_CSR_COMPACT")) h->csr_compact = atoi(e);
         if (const char* e = getenv("MOT_SORT_BITS")) h->rws.digit_bits = std::min(RS_MAX_BITS, std::max(4, atoi(e)));
         CK(dalloc(&h->d_blk, (size_t)32 * 1024));
         CK(dalloc(&h->d_bbox, (size_t)8));

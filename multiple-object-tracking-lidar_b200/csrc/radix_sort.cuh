@@ -11,6 +11,7 @@
 // No inter-block spin waits anywhere: a pass is three stream-ordered launches.
 #pragma once
 #include "common.cuh"
+#include "grid_uf.cuh"
 
 namespace mot {
 
@@ -93,16 +94,18 @@ __global__ void __launch_bounds__(256) k_rs_scan(const unsigned* __restrict__ hi
     if (lane == 31) tot[d] = (unsigned)incl;
 }
 
-constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes) {
-    return (size_t)(RS_WARPS + 2) * ((size_t)1 << bits) * 4 + 36 * 4 + (size_t)RS_TILE * 4 + (size_t)RS_TILE * key_bytes;
+constexpr int RS_ITEMS_BIG = 32;  // 8192-pair tiles for large inputs: 4x longer digit runs per tile (fewer partial sectors at L2)
+constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes, int items = RS_ITEMS) {
+    return (size_t)(RS_WARPS + 2) * ((size_t)1 << bits) * 4 + 36 * 4 + (size_t)RS_THREADS * items * 4 + (size_t)RS_THREADS * items * key_bytes;
 }
 
-template <typename KT, bool IOTA>
+template <typename KT, bool IOTA, int ITEMS = RS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                             KT* __restrict__ kout, uint32_t* __restrict__ vout, int n, int chunk,
                                                             int shift, int bits, const unsigned* __restrict__ prefix,
                                                             const unsigned* __restrict__ tot) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
+    constexpr int TILE = RS_THREADS * ITEMS;
     const int R = 1 << bits;
     const unsigned mask = R - 1;
     unsigned* cnt = reinterpret_cast<unsigned*>(rs_smem);  // [RS_WARPS][R]
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
     unsigned* gbase = tile_off + R;                        // [R]
     int* scan_tmp = reinterpret_cast<int*>(gbase + R);     // [36]
     uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 36);
-    KT* st_keys = reinterpret_cast<KT*>(st_vals + RS_TILE);
+    KT* st_keys = reinterpret_cast<KT*>(st_vals + TILE);
 
     const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const int G = gridDim.x, b = blockIdx.x;
@@ -138,16 +141,16 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
 
     const int begin = b * chunk;
     const int end = min(n, begin + chunk);
-    for (int tile_begin = begin; tile_begin < end; tile_begin += RS_TILE) {
+    for (int tile_begin = begin; tile_begin < end; tile_begin += TILE) {
         for (int i = tid; i < RS_WARPS * R; i += RS_THREADS) cnt[i] = 0;
         __syncthreads();
 
-        KT key[RS_ITEMS];
-        uint32_t val[RS_ITEMS];
-        unsigned rank[RS_ITEMS];
-        const int seg = tile_begin + w * (32 * RS_ITEMS);
+        KT key[ITEMS];
+        uint32_t val[ITEMS];
+        unsigned rank[ITEMS];
+        const int seg = tile_begin + w * (32 * ITEMS);
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
             const bool valid = idx < end;
             key[i] = valid ? kin[idx] : ~(KT)0;
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
         }
         unsigned* wcnt = cnt + w * R;
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
             const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;  // padding sorts last
             const unsigned peers = __match_any_sync(kFull, d);
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
         __syncthreads();
 
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
             const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;
             const unsigned pos = tile_off[d] + wcnt[d] + rank[i];
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
         }
         __syncthreads();
 
-        const int tile_n = min(RS_TILE, end - tile_begin);
+        const int tile_n = min(TILE, end - tile_begin);
         for (int j = tid; j < tile_n; j += RS_THREADS) {
             const KT k = st_keys[j];
             const unsigned d = (unsigned)((k >> shift) & mask);
@@ -486,6 +489,8 @@ struct RadixWorkspace {
     int* err_flag = nullptr;     // device int (bit 1: look-back spin limit hit)
     int mode = 0;                // 0 = three kernels per pass (default: faster at 1M-8M pairs on B200), 1 = onesweep
     int digit_bits = RS_MAX_BITS;  // widest digit of the three-kernel path (MOT_SORT_BITS, 4..10)
+    int big_tile_from = 1 << 22;   // inputs of at least this many pairs use 8192-pair scatter tiles (MOT_SORT_BIGTILE; 0 = never)
+    bool first_hist_done = false;  // the caller already produced pass 0's histogram (k_cell_keys_hist)
 };
 constexpr size_t rs_workspace_counters() { return (size_t)(1 << RS_MAX_BITS) * RS_MAX_GRID; }
 
@@ -502,7 +507,83 @@ inline cudaError_t rs_configure() {
     const int smem = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT));
     e = cudaFuncSetAttribute(k_rs_scatter<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_rs_scatter<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(k_rs_scatter<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const int smem_big = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT), RS_ITEMS_BIG);
+    e = cudaFuncSetAttribute(k_rs_scatter<KT, true, RS_ITEMS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_rs_scatter<KT, false, RS_ITEMS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
+}
+
+// pass / chunk plan of the three-kernel path (shared with k_cell_keys_hist, which produces pass 0's histogram itself)
+struct RsPlan {
+    int passes, base, rem;
+    bool big;
+    Chunking ck;
+    int bits0;  // digit width of pass 0
+};
+inline RsPlan rs_plan(int n, int key_bits, const RadixWorkspace& ws) {
+    RsPlan p;
+    if (key_bits < 1) key_bits = 1;
+    p.passes = (key_bits + ws.digit_bits - 1) / ws.digit_bits;
+    p.base = key_bits / p.passes;
+    p.rem = key_bits % p.passes;
+    p.big = ws.big_tile_from > 0 && n >= ws.big_tile_from;
+    p.ck = make_chunking(n, RS_THREADS * (p.big ? RS_ITEMS_BIG : RS_ITEMS), RS_MAX_GRID);
+    p.bits0 = p.base + (0 < p.rem ? 1 : 0);
+    return p;
+}
+
+// K1 + the first histogram of K2 in one pass: voxel key per point (fp64 cell coordinates, as k_cell_keys) written once and
+// counted for pass 0's digit while it is still in a register -- the separate k_rs_hist launch re-read all keys for that.
+// Same chunking as the sort (block b owns [b*chunk, (b+1)*chunk)), same histogram layout hist[d][b].
+template <typename KT>
+__global__ void __launch_bounds__(RS_THREADS) k_cell_keys_hist(const float4* __restrict__ pts, int m, int chunk, GridCodec g,
+                                                                const int* __restrict__ frame_offsets, KT* __restrict__ keys, int bits,
+                                                                unsigned* __restrict__ hist /* [R][G] */) {
+    extern __shared__ unsigned sh_hist[];
+    const int R = 1 << bits;
+    const unsigned mask = R - 1;
+    for (int d = threadIdx.x; d < R; d += RS_THREADS) sh_hist[d] = 0;
+    __syncthreads();
+    const int begin = blockIdx.x * chunk;
+    const int end = min(m, begin + chunk);
+    const int lane = lane_id();
+    for (int base = begin; base < end; base += RS_THREADS * 4) {
+        float4 p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            if (i < end) p[j] = ld_stream(pts + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = base + j * RS_THREADS + threadIdx.x;
+            const bool valid = i < end;
+            unsigned d = 0xffffffffu;
+            if (valid) {
+                int ix = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].x, g.minx), g.inv_e));
+                int iy = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].y, g.miny), g.inv_e));
+                int iz = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].z, g.minz), g.inv_e));
+                ix = min(max(ix, 0), g.nfx - 1);
+                iy = min(max(iy, 0), g.nfy - 1);
+                iz = min(max(iz, 0), g.nfz - 1);
+                const int frame = g.n_frames > 1 ? frame_of(frame_offsets, g.n_frames, i) : 0;
+                const KT key = key_compose<KT>(g, frame, ix, iy, iz);
+                keys[i] = key;
+                d = (unsigned)(key & (KT)mask);
+            }
+            const unsigned dp = __shfl_up_sync(kFull, d, 1);
+            const unsigned heads = __ballot_sync(kFull, lane == 0 || d != dp);
+            if (heads >> lane & 1u) {
+                const unsigned later = heads & ~((2u << lane) - 1u);
+                const int run = (later ? __ffs(later) - 1 : 32) - lane;
+                if (valid) atomicAdd(&sh_hist[d], (unsigned)run);
+            }
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < R; d += RS_THREADS) hist[(size_t)d * gridDim.x + blockIdx.x] = sh_hist[d];
 }
 
 // Sorts n pairs by the low `key_bits` bits of the key.  Input in (k[0], v[0]) -- v[0] is ignored and treated
@@ -541,25 +622,30 @@ inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, in
             return cur;
         }
     }
-    const int passes = (key_bits + ws.digit_bits - 1) / ws.digit_bits;
-    const int base = key_bits / passes, rem = key_bits % passes;
-    const Chunking ck = make_chunking(n, RS_TILE, RS_MAX_GRID);
+    const RsPlan pl = rs_plan(n, key_bits, ws);
+    const Chunking ck = pl.ck;
+    const bool big = pl.big;
     int cur = 0, shift = 0;
-    for (int p = 0; p < passes; ++p) {
-        const int bits = base + (p < rem ? 1 : 0);
+    for (int p = 0; p < pl.passes; ++p) {
+        const int bits = pl.base + (p < pl.rem ? 1 : 0);
         const int R = 1 << bits;
-        prof.begin(kid_base);
-        k_rs_hist<KT><<<ck.grid, RS_THREADS, R * sizeof(unsigned), st>>>(k[cur], n, ck.chunk, shift, bits, ws.hist);
-        prof.end();
+        if (!(p == 0 && ws.first_hist_done)) {
+            prof.begin(kid_base);
+            k_rs_hist<KT><<<ck.grid, RS_THREADS, R * sizeof(unsigned), st>>>(k[cur], n, ck.chunk, shift, bits, ws.hist);
+            prof.end();
+        }
         prof.begin(kid_base + 1);
         k_rs_scan<<<(R + 7) / 8, 256, 0, st>>>(ws.hist, ws.prefix, ws.tot, R, ck.grid);
         prof.end();
-        const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT));
+        const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT), big ? RS_ITEMS_BIG : RS_ITEMS);
         prof.begin(kid_base + 2);
-        if (p == 0 && iota_first)
-            k_rs_scatter<KT, true><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
-        else
-            k_rs_scatter<KT, false><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+        if (p == 0 && iota_first) {
+            if (big) k_rs_scatter<KT, true, RS_ITEMS_BIG><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+            else k_rs_scatter<KT, true><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+        } else {
+            if (big) k_rs_scatter<KT, false, RS_ITEMS_BIG><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+            else k_rs_scatter<KT, false><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+        }
         prof.end();
         cur ^= 1;
         shift += bits;

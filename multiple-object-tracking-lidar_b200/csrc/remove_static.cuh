@@ -184,6 +184,77 @@ constexpr int C1P_TILE = C1P_THREADS * C1P_ITEMS;
 constexpr unsigned C1P_AGG = 1u << 30, C1P_INCL = 2u << 30, C1P_VALUE = (1u << 30) - 1u;
 constexpr int C1P_SPIN_LIMIT = 1 << 24;  // a stuck look-back raises flag 2 instead of hanging the GPU
 
+// warp 0 of a tile: exclusive prefix of the tile's count over all preceding tiles (the tile's own aggregate is already
+// published); afterwards the tile's word holds its inclusive prefix.  Returns the prefix in every lane.
+__device__ __forceinline__ int c1p_lookback(unsigned* status, int tile, int tile_total, int* err_flag) {
+    int prefix = 0;
+    const int lane = lane_id();
+    int t = tile - 1, spins = 0;
+    while (t >= 0) {
+        const int mine = t - lane;
+        const unsigned sv = mine >= 0 ? __ldcg(status + mine) : C1P_INCL;  // before tile 0: an inclusive prefix of 0
+        const unsigned f = sv >> 30;
+        const unsigned incl_m = __ballot_sync(kFull, f == 2u), empty_m = __ballot_sync(kFull, f == 0u);
+        const int first_incl = incl_m ? __ffs(incl_m) - 1 : 32;                              // nearest predecessor holding an inclusive prefix
+        const unsigned need = first_incl >= 31 ? 0xffffffffu : ((2u << first_incl) - 1u);     // lanes 0 .. first_incl
+        if (empty_m & need) {
+            if (++spins > C1P_SPIN_LIMIT) { if (lane == 0) atomicOr(err_flag, 2); break; }
+            continue;
+        }
+        int v = ((need >> lane) & 1u) ? (int)(sv & C1P_VALUE) : 0;
+        v = warp_sum(v);
+        prefix += v;
+        if (incl_m) break;
+        t -= 32;
+    }
+    if (lane == 0) __stcg(status + tile, C1P_INCL | (unsigned)(prefix + tile_total));
+    return prefix;
+}
+
+// The same pass over 32-bit keys in index order: keeps (key, index) of every key != drop.  Used to shrink the CSR sort to the
+// points of the clusters that survive the size filter (cluster_table.cuh).
+__global__ void __launch_bounds__(C1P_THREADS) k_compact_keys_onepass(const uint32_t* __restrict__ keys, int n, uint32_t drop, uint32_t* __restrict__ kout,
+                                                                       uint32_t* __restrict__ vout, unsigned* status, int n_tiles,
+                                                                       int* __restrict__ err_flag) {
+    __shared__ int scratch[36];
+    __shared__ int s_tile, s_base;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(status + n_tiles, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= n_tiles) return;
+    const int i0 = tile * C1P_TILE + threadIdx.x * C1P_ITEMS;
+    uint32_t k[C1P_ITEMS];
+    unsigned keepm = 0;
+    if (i0 + C1P_ITEMS <= n) {  // two 16-byte loads (i0 is a multiple of 8)
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i0)), b = __ldg(reinterpret_cast<const uint4*>(keys + i0) + 1);
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+#pragma unroll
+        for (int j = 0; j < C1P_ITEMS; ++j) keepm |= (k[j] != drop ? 1u : 0u) << j;
+    } else {
+#pragma unroll
+        for (int j = 0; j < C1P_ITEMS; ++j) {
+            k[j] = i0 + j < n ? keys[i0 + j] : drop;
+            keepm |= (k[j] != drop ? 1u : 0u) << j;
+        }
+    }
+    int tile_total;
+    const int excl = block_exclusive_scan(__popc(keepm), scratch, &tile_total);
+    if (threadIdx.x == 0) __stcg(status + tile, (tile == 0 ? C1P_INCL : C1P_AGG) | (unsigned)tile_total);
+    if (warp_id() == 0) {
+        const int prefix = c1p_lookback(status, tile, tile_total, err_flag);
+        if (lane_id() == 0) s_base = prefix;
+    }
+    __syncthreads();
+    int w = s_base + excl;
+#pragma unroll
+    for (int j = 0; j < C1P_ITEMS; ++j)
+        if ((keepm >> j) & 1u) {
+            kout[w] = k[j];
+            vout[w] = (uint32_t)(i0 + j);
+            ++w;
+        }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(C1P_THREADS) k_compact_onepass(const float4* __restrict__ pts, int n, MapParams mp, const uint32_t* __restrict__ gbits,
                                                                   int use_smem, float4* __restrict__ out, unsigned* status /* [tiles] + ticket */,
@@ -229,29 +300,9 @@ __global__ void __launch_bounds__(C1P_THREADS) k_compact_onepass(const float4* _
     // publish, then look back (warp 0)
     if (threadIdx.x == 0) __stcg(status + tile, (tile == 0 ? C1P_INCL : C1P_AGG) | (unsigned)tile_total);
     if (warp_id() == 0) {
-        int prefix = 0;
-        const int lane = lane_id();
-        int t = tile - 1, spins = 0;
-        while (t >= 0) {
-            const int mine = t - lane;
-            const unsigned sv = mine >= 0 ? __ldcg(status + mine) : C1P_INCL;  // before tile 0: an inclusive prefix of 0
-            const unsigned f = sv >> 30;
-            const unsigned incl_m = __ballot_sync(kFull, f == 2u), empty_m = __ballot_sync(kFull, f == 0u);
-            const int first_incl = incl_m ? __ffs(incl_m) - 1 : 32;                 // nearest predecessor holding an inclusive prefix
-            const unsigned need = first_incl >= 31 ? 0xffffffffu : ((2u << first_incl) - 1u);  // lanes 0 .. first_incl
-            if (empty_m & need) {
-                if (++spins > C1P_SPIN_LIMIT) { if (lane == 0) atomicOr(err_flag, 2); break; }
-                continue;
-            }
-            int v = (need >> lane) & 1u ? (int)(sv & C1P_VALUE) : 0;
-            v = warp_sum(v);
-            prefix += v;
-            if (incl_m) break;
-            t -= 32;
-        }
-        if (lane == 0) {
+        const int prefix = c1p_lookback(status, tile, tile_total, err_flag);
+        if (lane_id() == 0) {
             s_base = prefix;
-            __stcg(status + tile, C1P_INCL | (unsigned)(prefix + tile_total));
             if (tile == n_tiles - 1) *total_out = prefix + tile_total;
         }
     }
