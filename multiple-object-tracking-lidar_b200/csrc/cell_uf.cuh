@@ -205,11 +205,78 @@ struct ClocWarpSmem {
     unsigned char code[CLOC_FINE];
 };
 
+// boxes of the batch are complete in sm: write them out and let every lane resolve its own coarse cell (warp level)
+__device__ __forceinline__ void cloc_finish(ClocWarpSmem& sm, int lane, bool valid, int ci, int f0, int f1, int F0, int nf,
+                                            const float4* __restrict__ spts, int* __restrict__ d_counts, float r2, int light,
+                                            int4* __restrict__ crec, float4* __restrict__ cbox, float4* __restrict__ fbox, int* __restrict__ parent,
+                                            int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap) {
+    for (int x = lane; x < nf; x += 32) {
+        const int st = sm.start[x];
+        fbox[2 * (size_t)(F0 + x)] = make_float4(sm.mn[0][x], sm.mn[1][x], sm.mn[2][x], __int_as_float(st));
+        fbox[2 * (size_t)(F0 + x) + 1] = make_float4(sm.mx[0][x], sm.mx[1][x], sm.mx[2][x], __int_as_float(sm.start[x + 1] - st));
+    }
+    if (!valid) return;
+    const int l0 = f0 - F0, n_a = f1 - f0;
+    auto lo_of = [&](int x) { return make_float4(sm.mn[0][x], sm.mn[1][x], sm.mn[2][x], __int_as_float(sm.start[x])); };
+    auto hi_of = [&](int x) { return make_float4(sm.mx[0][x], sm.mx[1][x], sm.mx[2][x], __int_as_float(sm.start[x + 1] - sm.start[x])); };
+    unsigned mask = 0;
+    float c_mn0 = INFINITY, c_mn1 = INFINITY, c_mn2 = INFINITY, c_mx0 = -INFINITY, c_mx1 = -INFINITY, c_mx2 = -INFINITY;
+    for (int k = 0; k < n_a; ++k) {
+        const int x = l0 + k;
+        mask |= 1u << sm.code[x];
+        c_mn0 = fminf(c_mn0, sm.mn[0][x]); c_mn1 = fminf(c_mn1, sm.mn[1][x]); c_mn2 = fminf(c_mn2, sm.mn[2][x]);
+        c_mx0 = fmaxf(c_mx0, sm.mx[0][x]); c_mx1 = fmaxf(c_mx1, sm.mx[1][x]); c_mx2 = fmaxf(c_mx2, sm.mx[2][x]);
+    }
+    cbox[2 * (size_t)ci] = make_float4(c_mn0, c_mn1, c_mn2, 0.0f);
+    cbox[2 * (size_t)ci + 1] = make_float4(c_mx0, c_mx1, c_mx2, 0.0f);
+    // connected components among the children (all of them are ring-1 neighbours of each other)
+    unsigned lab = 0x76543210u;  // 4 bits per child rank: smallest rank of its component
+    for (int i = 0; i < n_a - 1; ++i) {
+        const float4 alo = lo_of(l0 + i), ahi = hi_of(l0 + i);
+        for (int j = i + 1; j < n_a; ++j) {
+            const unsigned li = (lab >> (4 * i)) & 15u, lj = (lab >> (4 * j)) & 15u;
+            if (li == lj) continue;
+            UFSTAT(ST_LOCAL_PAIRS, 1);
+            const float4 blo = lo_of(l0 + j), bhi = hi_of(l0 + j);
+            if (!fine_pair(spts, alo, ahi, blo, bhi, f0 + i, f0 + j, 1, r2, light, heavy1, heavy2, heavy_cap, d_counts)) continue;
+            const unsigned lo = min(li, lj), hi = max(li, lj);
+            for (int k = 0; k < n_a; ++k)
+                if (((lab >> (4 * k)) & 15u) == hi) lab = (lab & ~(15u << (4 * k))) | (lo << (4 * k));
+        }
+    }
+    unsigned lab3 = 0;
+    for (int k = 0; k < n_a; ++k) {
+        const unsigned l = (lab >> (4 * k)) & 15u;
+        lab3 |= l << (3 * k);
+        parent[f0 + k] = f0 + (int)l;
+    }
+    crec[ci] = make_int4(sm.start[l0], sm.start[l0 + n_a] - sm.start[l0], f0, (int)(mask | (lab3 << 8)));
+}
+
+// segmented min / max scan over the lanes of one 32-point group (points of a fine cell are consecutive lanes); on return the
+// LAST lane of every run holds the run's box
+__device__ __forceinline__ void cloc_scan(int lf, float& ax, float& ay, float& az, float& bx, float& by, float& bz) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int lo_ = __shfl_up_sync(kFull, lf, o);
+        const float tax = __shfl_up_sync(kFull, ax, o), tay = __shfl_up_sync(kFull, ay, o), taz = __shfl_up_sync(kFull, az, o);
+        const float tbx = __shfl_up_sync(kFull, bx, o), tby = __shfl_up_sync(kFull, by, o), tbz = __shfl_up_sync(kFull, bz, o);
+        if (lane >= o && lo_ == lf) {
+            ax = fminf(ax, tax); ay = fminf(ay, tay); az = fminf(az, taz);
+            bx = fmaxf(bx, tbx); by = fmaxf(by, tby); bz = fmaxf(bz, tbz);
+        }
+    }
+}
+
+constexpr int CLOC_DENSE_POINTS = 2048;  // a batch with more points goes to k_cell_local_dense (a whole CTA per batch)
+
 __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __restrict__ spts, const int* __restrict__ fc_start,
                                                               const int* __restrict__ cc_first, const unsigned char* __restrict__ fcode,
                                                               int* __restrict__ d_counts, float r2, int light, int4* __restrict__ crec,
                                                               float4* __restrict__ cbox, float4* __restrict__ fbox, int* __restrict__ parent,
-                                                              int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap) {
+                                                              int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap,
+                                                              int* __restrict__ dense_list, int dense_cap) {
     __shared__ ClocWarpSmem sm_all[CLOC_WARPS];
     ClocWarpSmem& sm = sm_all[warp_id()];
     const int n_coarse = d_counts[CNT_COARSE];
@@ -226,6 +293,20 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
         }
         const int F0 = __shfl_sync(kFull, f0, 0), F1 = __shfl_sync(kFull, f1, nvalid - 1);
         const int nf = F1 - F0;  // <= 256
+        // densely sampled surfaces (thousands of points in these 32 cells): one warp walking them is the tail of the launch
+        if (dense_list) {
+            int pe = 0;
+            if (lane == 0) pe = __ldg(fc_start + F1) - __ldg(fc_start + F0);
+            pe = __shfl_sync(kFull, pe, 0);
+            if (pe > CLOC_DENSE_POINTS) {
+                if (lane == 0) {
+                    const int slot = atomicAdd(&d_counts[CNT_DENSE], 1);
+                    if (slot < dense_cap) dense_list[slot] = c0;
+                    else atomicOr(&d_counts[CNT_FLAGS], 1);  // cannot happen: the list holds a batch per 2048 points
+                }
+                continue;
+            }
+        }
         for (int x = lane; x < nf; x += 32) {
             sm.mn[0][x] = INFINITY; sm.mn[1][x] = INFINITY; sm.mn[2][x] = INFINITY;
             sm.mx[0][x] = -INFINITY; sm.mx[1][x] = -INFINITY; sm.mx[2][x] = -INFINITY;
@@ -234,9 +315,8 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
         for (int x = lane; x <= nf; x += 32) sm.start[x] = __ldg(fc_start + F0 + x);
         __syncwarp();
         const int P0 = sm.start[0], P1 = sm.start[nf];
-        // Points of a fine cell are consecutive lanes: a segmented min/max scan over the lanes (shuffles, every lane busy), the
-        // last lane of each run folds the run into the cell's box.  This warp is the only writer of its boxes and a cell has
-        // one tail lane per group, so the fold is a plain read-modify-write.
+        // This warp is the only writer of its boxes and a cell has one tail lane per group, so the fold is a plain
+        // read-modify-write.
         for (int jb = P0; jb < P1; jb += 32 * CLOC_UNROLL) {
             float4 pts[CLOC_UNROLL];
 #pragma unroll
@@ -249,16 +329,7 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
                 if (jb + 32 * u >= P1) break;  // warp uniform
                 const int lf = __float_as_int(pts[u].w) - F0;  // lanes past the end: negative, no cell
                 float ax = pts[u].x, ay = pts[u].y, az = pts[u].z, bx = ax, by = ay, bz = az;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int lo_ = __shfl_up_sync(kFull, lf, o);
-                    const float tax = __shfl_up_sync(kFull, ax, o), tay = __shfl_up_sync(kFull, ay, o), taz = __shfl_up_sync(kFull, az, o);
-                    const float tbx = __shfl_up_sync(kFull, bx, o), tby = __shfl_up_sync(kFull, by, o), tbz = __shfl_up_sync(kFull, bz, o);
-                    if (lane >= o && lo_ == lf) {
-                        ax = fminf(ax, tax); ay = fminf(ay, tay); az = fminf(az, taz);
-                        bx = fmaxf(bx, tbx); by = fmaxf(by, tby); bz = fmaxf(bz, tbz);
-                    }
-                }
+                cloc_scan(lf, ax, ay, az, bx, by, bz);
                 const int lnext = __shfl_down_sync(kFull, lf, 1);
                 if (jb + 32 * u + lane < P1 && (lane == 31 || lnext != lf)) {
                     sm.mn[0][lf] = fminf(sm.mn[0][lf], ax); sm.mn[1][lf] = fminf(sm.mn[1][lf], ay); sm.mn[2][lf] = fminf(sm.mn[2][lf], az);
@@ -268,49 +339,73 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
             }
         }
         __syncwarp();
-        for (int x = lane; x < nf; x += 32) {
-            const int st = sm.start[x];
-            fbox[2 * (size_t)(F0 + x)] = make_float4(sm.mn[0][x], sm.mn[1][x], sm.mn[2][x], __int_as_float(st));
-            fbox[2 * (size_t)(F0 + x) + 1] = make_float4(sm.mx[0][x], sm.mx[1][x], sm.mx[2][x], __int_as_float(sm.start[x + 1] - st));
-        }
-        if (valid) {
-            const int l0 = f0 - F0, n_a = f1 - f0;
-            auto lo_of = [&](int x) { return make_float4(sm.mn[0][x], sm.mn[1][x], sm.mn[2][x], __int_as_float(sm.start[x])); };
-            auto hi_of = [&](int x) { return make_float4(sm.mx[0][x], sm.mx[1][x], sm.mx[2][x], __int_as_float(sm.start[x + 1] - sm.start[x])); };
-            unsigned mask = 0;
-            float c_mn0 = INFINITY, c_mn1 = INFINITY, c_mn2 = INFINITY, c_mx0 = -INFINITY, c_mx1 = -INFINITY, c_mx2 = -INFINITY;
-            for (int k = 0; k < n_a; ++k) {
-                const int x = l0 + k;
-                mask |= 1u << sm.code[x];
-                c_mn0 = fminf(c_mn0, sm.mn[0][x]); c_mn1 = fminf(c_mn1, sm.mn[1][x]); c_mn2 = fminf(c_mn2, sm.mn[2][x]);
-                c_mx0 = fmaxf(c_mx0, sm.mx[0][x]); c_mx1 = fmaxf(c_mx1, sm.mx[1][x]); c_mx2 = fmaxf(c_mx2, sm.mx[2][x]);
-            }
-            cbox[2 * (size_t)ci] = make_float4(c_mn0, c_mn1, c_mn2, 0.0f);
-            cbox[2 * (size_t)ci + 1] = make_float4(c_mx0, c_mx1, c_mx2, 0.0f);
-            // connected components among the children (all of them are ring-1 neighbours of each other)
-            unsigned lab = 0x76543210u;  // 4 bits per child rank: smallest rank of its component
-            for (int i = 0; i < n_a - 1; ++i) {
-                const float4 alo = lo_of(l0 + i), ahi = hi_of(l0 + i);
-                for (int j = i + 1; j < n_a; ++j) {
-                    const unsigned li = (lab >> (4 * i)) & 15u, lj = (lab >> (4 * j)) & 15u;
-                    if (li == lj) continue;
-                    UFSTAT(ST_LOCAL_PAIRS, 1);
-                    const float4 blo = lo_of(l0 + j), bhi = hi_of(l0 + j);
-                    if (!fine_pair(spts, alo, ahi, blo, bhi, f0 + i, f0 + j, 1, r2, light, heavy1, heavy2, heavy_cap, d_counts)) continue;
-                    const unsigned lo = min(li, lj), hi = max(li, lj);
-                    for (int k = 0; k < n_a; ++k)
-                        if (((lab >> (4 * k)) & 15u) == hi) lab = (lab & ~(15u << (4 * k))) | (lo << (4 * k));
-                }
-            }
-            unsigned lab3 = 0;
-            for (int k = 0; k < n_a; ++k) {
-                const unsigned l = (lab >> (4 * k)) & 15u;
-                lab3 |= l << (3 * k);
-                parent[f0 + k] = f0 + (int)l;
-            }
-            crec[ci] = make_int4(sm.start[l0], sm.start[l0 + n_a] - sm.start[l0], f0, (int)(mask | (lab3 << 8)));
-        }
+        cloc_finish(sm, lane, valid, ci, f0, f1, F0, nf, spts, d_counts, r2, light, crec, cbox, fbox, parent, heavy1, heavy2, heavy_cap);
         __syncwarp();
+    }
+}
+
+// The batches k_cell_local handed over: one CTA per batch.  All warps sweep the batch's points (same segmented scan; the
+// tail lane of a run folds it into the cell's box with shared-memory atomics on order-preserving ints, several warps may
+// meet in one cell), then warp 0 finishes the batch exactly as k_cell_local does.
+constexpr int CLD_THREADS = 512;
+__global__ void __launch_bounds__(CLD_THREADS) k_cell_local_dense(const float4* __restrict__ spts, const int* __restrict__ fc_start,
+                                                                   const int* __restrict__ cc_first, const unsigned char* __restrict__ fcode,
+                                                                   int* __restrict__ d_counts, float r2, int light, int4* __restrict__ crec,
+                                                                   float4* __restrict__ cbox, float4* __restrict__ fbox, int* __restrict__ parent,
+                                                                   int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap,
+                                                                   const int* __restrict__ dense_list, int dense_cap) {
+    __shared__ ClocWarpSmem sm;
+    __shared__ int imn[3][CLOC_FINE], imx[3][CLOC_FINE];
+    __shared__ int s_f[2];
+    const int n_coarse = d_counts[CNT_COARSE];
+    const int n_list = min(d_counts[CNT_DENSE], dense_cap);
+    const int lane = lane_id();
+    for (int e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const int c0 = dense_list[e];
+        const int nvalid = min(32, n_coarse - c0);
+        if (threadIdx.x == 0) {
+            s_f[0] = __ldg(cc_first + c0);
+            s_f[1] = __ldg(cc_first + c0 + nvalid);
+        }
+        __syncthreads();
+        const int F0 = s_f[0], F1 = s_f[1], nf = F1 - F0;
+        for (int x = threadIdx.x; x < nf; x += CLD_THREADS) {
+            imn[0][x] = 0x7fffffff; imn[1][x] = 0x7fffffff; imn[2][x] = 0x7fffffff;
+            imx[0][x] = (int)0x80000000; imx[1][x] = (int)0x80000000; imx[2][x] = (int)0x80000000;
+            sm.code[x] = fcode[F0 + x];
+        }
+        for (int x = threadIdx.x; x <= nf; x += CLD_THREADS) sm.start[x] = __ldg(fc_start + F0 + x);
+        __syncthreads();
+        const int P0 = sm.start[0], P1 = sm.start[nf];
+        for (int jb = P0 + warp_id() * 32; jb < P1; jb += CLD_THREADS) {  // every warp: its 32-point groups, stride = CTA
+            const int j = jb + lane;
+            const float4 p = j < P1 ? ld_stream(spts + j) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            const int lf = __float_as_int(p.w) - F0;
+            float ax = p.x, ay = p.y, az = p.z, bx = ax, by = ay, bz = az;
+            cloc_scan(lf, ax, ay, az, bx, by, bz);
+            const int lnext = __shfl_down_sync(kFull, lf, 1);
+            if (j < P1 && (lane == 31 || lnext != lf)) {
+                atomicMin(&imn[0][lf], float_to_ordered(ax)); atomicMin(&imn[1][lf], float_to_ordered(ay)); atomicMin(&imn[2][lf], float_to_ordered(az));
+                atomicMax(&imx[0][lf], float_to_ordered(bx)); atomicMax(&imx[1][lf], float_to_ordered(by)); atomicMax(&imx[2][lf], float_to_ordered(bz));
+            }
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < nf; x += CLD_THREADS) {
+            sm.mn[0][x] = ordered_to_float_bits(imn[0][x]); sm.mn[1][x] = ordered_to_float_bits(imn[1][x]); sm.mn[2][x] = ordered_to_float_bits(imn[2][x]);
+            sm.mx[0][x] = ordered_to_float_bits(imx[0][x]); sm.mx[1][x] = ordered_to_float_bits(imx[1][x]); sm.mx[2][x] = ordered_to_float_bits(imx[2][x]);
+        }
+        __syncthreads();
+        if (warp_id() == 0) {
+            const int ci = c0 + lane;
+            const bool valid = ci < n_coarse;
+            int f0 = 0, f1 = 0;
+            if (valid) {
+                f0 = __ldg(cc_first + ci);
+                f1 = __ldg(cc_first + ci + 1);
+            }
+            cloc_finish(sm, lane, valid, ci, f0, f1, F0, nf, spts, d_counts, r2, light, crec, cbox, fbox, parent, heavy1, heavy2, heavy_cap);
+        }
+        __syncthreads();
     }
 }
 
@@ -825,9 +920,14 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
             __syncwarp();
         }
     };
-    for (int row = 0; row < 5; ++row) {
+    // work items = (neighbour row, batch of 32 cells), row-major: faces first, and a warp of a small launch gets its share of
+    // ALL rows instead of walking the five rows one after the other (that serial chain was the single-frame latency)
+    const int n_batches = (n_coarse + 31) >> 5;
+    for (long long item = blockIdx.x * UFF_WARPS + warp_id(); item < 5ll * n_batches; item += n_warps) {
+        const int row = (int)(item / n_batches);
         const int dy = c_row_dy[row], dz = c_row_dz[row];
-        for (int base = (blockIdx.x * UFF_WARPS + warp_id()) * 32; base < n_coarse; base += n_warps * 32) {
+        {
+            const int base = (int)(item - (long long)row * n_batches) * 32;
             const int A = base + lane;
             int nb0 = -1, nb1 = -1, nb2 = -1;  // neighbour cells of this row at dx = 0, -1, +1 (centre first: it is the face neighbour)
             if (A < n_coarse) {

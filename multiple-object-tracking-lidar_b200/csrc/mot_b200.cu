@@ -52,7 +52,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -60,7 +60,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense"};
 
 struct mot_handle {
     int device = 0;
@@ -132,6 +132,7 @@ struct mot_handle {
     float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
     int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
     int heavy_cap = 0;
+    int cell_dense = 1;     // batches of > 2048 points go to k_cell_local_dense (MOT_CELL_DENSE=0: one warp walks any batch)
     int uf_light = 256;     // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
     int uf_cross_blocks = 4;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
     int uf_split = 0;        // MOT_UF_SPLIT=1: face rows and the remaining rows as two launches
@@ -366,9 +367,18 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
         }
         int lgrid = (M + CLOC_THREADS - 1) / CLOC_THREADS;
         if (lgrid > h->num_sms * 7) lgrid = h->num_sms * 7;
+        int* dlist = h->cell_dense ? h->d_dense_list : nullptr;
         LAUNCH(KID_CELL_LOCAL, k_cell_local<<<lgrid, CLOC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2, h->uf_light,
-                                                                               h->d_crec, h->d_cbox, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
-                                                                               h->heavy_cap));
+                                                                           h->d_crec, h->d_cbox, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
+                                                                           h->heavy_cap, dlist, h->dense_cap));
+        if (dlist) {
+            int dgrid = (M + CLOC_DENSE_POINTS - 1) / CLOC_DENSE_POINTS;
+            if (dgrid > h->num_sms * 3) dgrid = h->num_sms * 3;
+            LAUNCH(KID_CELL_LOCAL_DENSE, k_cell_local_dense<<<dgrid, CLD_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2,
+                                                                                         h->uf_light, h->d_crec, h->d_cbox, h->d_fbox, h->d_parent,
+                                                                                         h->d_heavy1, h->d_heavy2, h->heavy_cap, h->d_dense_list,
+                                                                                         h->dense_cap));
+        }
         if (h->uf_xmode == 2) {
             int fgrid = (M + UFF_THREADS - 1) / UFF_THREADS;
             if (fgrid > h->num_sms * h->uf_fused_blocks) fgrid = h->num_sms * h->uf_fused_blocks;
@@ -782,6 +792,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->heavy_cap = (int)(n / 2 + 4096);
         CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
         CK(dalloc(&h->d_heavy2, (size_t)h->heavy_cap));
+        if (const char* e = getenv("MOT_CELL_DENSE")) h->cell_dense = atoi(e);
         if (const char* e = getenv("MOT_UF_AUTO")) h->uf_auto_points = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
         if (const char* e = getenv("MOT_UF_XBLOCKS")) h->uf_cross_blocks = std::min(32, std::max(1, atoi(e)));
