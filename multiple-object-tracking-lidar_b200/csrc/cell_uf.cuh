@@ -894,7 +894,8 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
                                                                            const float4* __restrict__ fbox, const float4* __restrict__ spts,
                                                                            const KT* __restrict__ hkeys, const int* __restrict__ hvals,
                                                                            int* __restrict__ d_counts, int* parent, GridCodec g, float r2, int light,
-                                                                           int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap) {
+                                                                           int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap,
+                                                                           int row_inner) {
     __shared__ int4 s_queue[UFF_WARPS][UFF_QUEUE];
     int4* q = s_queue[warp_id()];
     int qn = 0;  // warp uniform
@@ -924,10 +925,12 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
     // ALL rows instead of walking the five rows one after the other (that serial chain was the single-frame latency)
     const int n_batches = (n_coarse + 31) >> 5;
     for (long long item = blockIdx.x * UFF_WARPS + warp_id(); item < 5ll * n_batches; item += n_warps) {
-        const int row = (int)(item / n_batches);
+        // row_inner = 0: row-major (all cells for the face rows first: most root skips, but five sweeps over the cell tables);
+        // 1: the five rows of a batch of cells one after the other (one sweep: the tables of a batch stay in L1 / L2)
+        const int row = row_inner ? (int)(item % 5) : (int)(item / n_batches);
         const int dy = c_row_dy[row], dz = c_row_dz[row];
         {
-            const int base = (int)(item - (long long)row * n_batches) * 32;
+            const int base = (row_inner ? (int)(item / 5) : (int)(item - (long long)row * n_batches)) * 32;
             const int A = base + lane;
             int nb0 = -1, nb1 = -1, nb2 = -1;  // neighbour cells of this row at dx = 0, -1, +1 (centre first: it is the face neighbour)
             if (A < n_coarse) {

@@ -132,6 +132,7 @@ struct mot_handle {
     float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
     int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
     int heavy_cap = 0;
+    int uf_row_inner = 0;   // MOT_UF_ROWINNER: k_uf_fused item order (see the kernel)
     int cell_dense = 1;     // batches of > 2048 points go to k_cell_local_dense (MOT_CELL_DENSE=0: one warp walks any batch)
     int uf_light = 256;     // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
     int uf_cross_blocks = 4;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
@@ -384,7 +385,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             if (fgrid > h->num_sms * h->uf_fused_blocks) fgrid = h->num_sms * h->uf_fused_blocks;
             LAUNCH(KID_UF_FUSED, k_uf_fused<KT><<<fgrid, UFF_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec, h->d_fbox, h->d_spts,
                                                                               reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts, h->d_parent,
-                                                                              g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap));
+                                                                              g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, h->uf_row_inner));
         } else if (h->uf_xmode == 1) {
             int sgrid = (M + UFS_THREADS - 1) / UFS_THREADS;
             if (sgrid > h->num_sms * 8) sgrid = h->num_sms * 8;
@@ -792,6 +793,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->heavy_cap = (int)(n / 2 + 4096);
         CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
         CK(dalloc(&h->d_heavy2, (size_t)h->heavy_cap));
+        if (const char* e = getenv("MOT_UF_ROWINNER")) h->uf_row_inner = atoi(e);
         if (const char* e = getenv("MOT_CELL_DENSE")) h->cell_dense = atoi(e);
         if (const char* e = getenv("MOT_UF_AUTO")) h->uf_auto_points = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
