@@ -151,3 +151,29 @@ def test_remove_static_two_pass_matches_one_pass(mot, oracle, synth):
     assert np.array_equal(a, ref) and np.array_equal(b, ref)
     t0.close()
     t1.close()
+
+
+def test_batch_run_across_gpus(mot, oracle, synth):
+    # one handle per GPU (skipped on a single-GPU box): the merged tables, written to host memory, equal one handle's batch call
+    import torch
+    n_gpus = torch.cuda.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs at least two GPUs")
+    occ, resn, origin = synth.make_map_c1()
+    p = synth.C1_PARAMS
+    clouds = _frames_c1(synth, 9, n_points=15000)
+    stamps = np.linspace(0.5, 1.3, len(clouds)).astype(np.float32)
+    total = sum(len(c) for c in clouds)
+    trks = [mot.Tracker(device=g, max_points=total + 16, max_tracks=0) for g in range(min(n_gpus, 4))]
+    for t in trks:
+        t.set_map(occ, resn, origin[:2], static_tolarance=p["static_tolerance"])
+        t.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    one = trks[0].frame_batch(clouds, do_remove_static=True, stamps=stamps)
+    many = mot.batch_run(trks, clouds, do_remove_static=True, stamps=stamps, packed12=True)
+    for key in ("frame_kept_offsets", "frame_cluster_offsets", "offsets", "indices"):
+        assert np.array_equal(many[key], one[key]), key
+    assert np.array_equal(many["centroids"].view(np.uint32), one["centroids"].view(np.uint32))
+    assert many["stats"].tobytes() == one["stats"].tobytes()
+    _check_batch_against_oracle(many, clouds, oracle, occ, resn, origin, p, stamps)
+    for t in trks:
+        t.close()
