@@ -44,6 +44,14 @@ __device__ unsigned long long g_uf_stats[ST_N];
 #define UFSTAT_MAX(i, v) ((void)0)
 #endif
 
+// ---- self checks (build with -DMOT_CHECKS): compute-sanitizer is closed on the GPU pool, so the index arithmetic of this file
+// can be checked by a build of its own -- every violated bound raises flag 16 (the host then fails the call with MOT_ERR_CUDA) ----
+#ifdef MOT_CHECKS
+#define MOT_CHECK(cond, d_counts) do { if (!(cond)) atomicOr((d_counts) + CNT_FLAGS, 16); } while (0)
+#else
+#define MOT_CHECK(cond, d_counts) ((void)0)
+#endif
+
 // ---- union-find primitives of this generation -----------------------------------------------------------------------------
 // MOT_UF_HOOK = 0: larger index under smaller (atomicMin), as grid_uf.cuh.  = 1 (default): the root whose BIT-REVERSED index
 // is larger goes under the other (atomicCAS on a root).  Hooking by plain index turns a run of x-adjacent cells -- all united
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
         }
         const int F0 = __shfl_sync(kFull, f0, 0), F1 = __shfl_sync(kFull, f1, nvalid - 1);
         const int nf = F1 - F0;  // <= 256
+        MOT_CHECK(nf >= 1 && nf <= CLOC_FINE && F0 >= 0 && F1 <= d_counts[CNT_FINE], d_counts);
         // densely sampled surfaces (thousands of points in these 32 cells): one warp walking them is the tail of the launch
         if (dense_list) {
             int pe = 0;
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(CLOC_THREADS) k_cell_local(const float4* __res
             for (int u = 0; u < CLOC_UNROLL; ++u) {
                 if (jb + 32 * u >= P1) break;  // warp uniform
                 const int lf = __float_as_int(pts[u].w) - F0;  // lanes past the end: negative, no cell
+                MOT_CHECK(jb + 32 * u + lane >= P1 || (lf >= 0 && lf < nf), d_counts);
                 float ax = pts[u].x, ay = pts[u].y, az = pts[u].z, bx = ax, by = ay, bz = az;
                 cloc_scan(lf, ax, ay, az, bx, by, bz);
                 const int lnext = __shfl_down_sync(kFull, lf, 1);
@@ -381,6 +391,7 @@ __global__ void __launch_bounds__(CLD_THREADS) k_cell_local_dense(const float4* 
             const int j = jb + lane;
             const float4 p = j < P1 ? ld_stream(spts + j) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
             const int lf = __float_as_int(p.w) - F0;
+            MOT_CHECK(j >= P1 || (lf >= 0 && lf < nf), d_counts);
             float ax = p.x, ay = p.y, az = p.z, bx = ax, by = ay, bz = az;
             cloc_scan(lf, ax, ay, az, bx, by, bz);
             const int lnext = __shfl_down_sync(kFull, lf, 1);
@@ -848,6 +859,7 @@ __device__ __forceinline__ void walk_step(WalkLane& w, const float4* __restrict_
     const int j = __popc(mB & ((1u << cb) - 1u));
     const int fa = w.f0A + (int)i, fb = w.f0B + j;
     const int la = w.f0A + (int)((w.labA >> (3 * i)) & 7u), lb = w.f0B + (int)((w.labB >> (3 * j)) & 7u);  // local roots
+    MOT_CHECK(fa >= 0 && fb >= 0 && fa < d_counts[CNT_FINE] && fb < d_counts[CNT_FINE] && la <= fa && lb <= fb && la >= w.f0A && lb >= w.f0B, d_counts);
     const float4 alo = __ldg(fbox + 2 * (size_t)fa), ahi = __ldg(fbox + 2 * (size_t)fa + 1);
     const float4 blo = __ldg(fbox + 2 * (size_t)fb), bhi = __ldg(fbox + 2 * (size_t)fb + 1);
     int pa = 0, pb = 0;
@@ -914,7 +926,11 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
             if (all ? (qn == 0 && n_live == 0) : (qn + n_live < 32)) break;
             const int take = min(qn, __popc(idle));
             const int k = __popc(idle & lanemask_lt());
-            if (!(w.misc & 1u) && k < take) walk_load(w, crec, q[qn - 1 - k]);
+            MOT_CHECK(qn >= 0 && qn <= UFF_QUEUE, d_counts);
+            if (!(w.misc & 1u) && k < take) {
+                MOT_CHECK(q[qn - 1 - k].x >= 0 && q[qn - 1 - k].x < n_coarse && q[qn - 1 - k].y >= 0 && q[qn - 1 - k].y < n_coarse, d_counts);
+                walk_load(w, crec, q[qn - 1 - k]);
+            }
             qn -= take;
             __syncwarp();
             if (w.misc & 1u) walk_step(w, fbox, spts, parent, r2, light, heavy1, heavy2, heavy_cap, d_counts);
@@ -1001,6 +1017,7 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
             if (keep & 2u) q[slot++] = make_int4(A, nb1, 0 | dcode, 0);
             if (keep & 4u) q[slot++] = make_int4(A, nb2, 2 | dcode, 0);
             qn += __shfl_sync(kFull, incl, 31);
+            MOT_CHECK(qn <= UFF_QUEUE, d_counts);
             __syncwarp();
             drain(false);
         }

@@ -552,6 +552,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_total = total;
     std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
+    if (h->h_pinned[8 + CNT_FLAGS] & 16) return fail(h, MOT_ERR_CUDA, "internal self check failed (MOT_CHECKS build): an index left its bounds in cell_uf.cuh");
     if (h->h_pinned[8 + CNT_FLAGS] & 8) return fail(h, MOT_ERR_CUDA, "TMA staging of a cell tile timed out (mbarrier never completed)");
     if (h->h_pinned[8 + CNT_FLAGS] & 4) return fail(h, MOT_ERR_CAPACITY, "cell-pair task list overflow (internal capacity)");
     if (h->h_pinned[8 + CNT_FLAGS] & 2) return fail(h, MOT_ERR_CUDA, "radix sort look-back exceeded its spin limit");

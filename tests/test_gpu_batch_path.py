@@ -177,3 +177,54 @@ def test_batch_run_across_gpus(mot, oracle, synth):
     _check_batch_against_oracle(many, clouds, oracle, occ, resn, origin, p, stamps)
     for t in trks:
         t.close()
+
+
+def _labels_parallel(oracle, clouds, tol, threads=8):
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(threads) as ex:   # the oracle is a C library: ctypes releases the GIL
+        return list(ex.map(lambda c: oracle.labels_grid(c, tol), clouds))
+
+
+def test_c3_full_shape(mot, oracle, synth):
+    # BASELINE config 3 at the per-GPU shape of the 8-GPU run: 64 frames x 130k points in ONE batch call; every frame's
+    # component labels against the oracle (full-size shapes under -m gpu)
+    p3 = synth.C3_PARAMS
+    sc3 = synth.scene_c3()
+    nf = 64
+    frames = [sc3.frame(f, n_points=synth.C3_POINTS) for f in range(nf)]
+    t = mot.Tracker(device=0, max_points=nf * synth.C3_POINTS, max_tracks=0)
+    t.set_cluster_params(p3["cluster_tolerance"], p3["min_cluster_size"], p3["max_cluster_size"])
+    fco, off, idx = t.extract_batch(frames)
+    lab = t.result_labels()
+    refs = _labels_parallel(oracle, frames, p3["cluster_tolerance"])
+    for f in range(nf):
+        assert np.array_equal(lab[f * synth.C3_POINTS:(f + 1) * synth.C3_POINTS], refs[f] + f * synth.C3_POINTS), f"frame {f}"
+    for f in (0, 31, 63):   # and the CSR of a few frames
+        o_ref, i_ref = oracle.csr_from_labels(refs[f], p3["min_cluster_size"], p3["max_cluster_size"])
+        k0, k1 = fco[f], fco[f + 1]
+        assert np.array_equal(off[k0:k1 + 1] - off[k0], o_ref) and np.array_equal(idx[off[k0]:off[k1]], i_ref)
+    t.close()
+
+
+def test_c4_full_shape(mot, oracle, synth):
+    # BASELINE config 4 at full size: 2^22 points, 2,000 blobs, tolerance 0.1 / 0.3 / 1.0 (sparse cells ... hundreds of points per
+    # cell, heavy witness lists); labels and CSR against the oracle
+    p4 = synth.C4_PARAMS
+    f4 = synth.make_frame_c4()
+    tols = (0.1, 0.3, 1.0)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(3) as ex:
+        futs = {tol: ex.submit(oracle.labels_grid, f4, tol) for tol in tols}
+        t = mot.Tracker(device=0, max_points=len(f4), max_tracks=0)
+        got = {}
+        for tol in tols:
+            t.set_cluster_params(tol, p4["min_cluster_size"], p4["max_cluster_size"])
+            off, idx = t.extract(f4)
+            got[tol] = (t.result_labels(), off, idx)
+        t.close()
+        for tol in tols:
+            ref = futs[tol].result()
+            lab, off, idx = got[tol]
+            assert np.array_equal(lab, ref), f"tol {tol}: labels"
+            o_ref, i_ref = oracle.csr_from_labels(ref, p4["min_cluster_size"], p4["max_cluster_size"])
+            assert np.array_equal(off, o_ref) and np.array_equal(idx, i_ref), f"tol {tol}: CSR"
