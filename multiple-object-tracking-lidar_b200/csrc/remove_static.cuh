@@ -213,30 +213,33 @@ __device__ __forceinline__ int c1p_lookback(unsigned* status, int tile, int tile
 
 // The same pass over 32-bit keys in index order: keeps (key, index) of every key != drop.  Used to shrink the CSR sort to the
 // points of the clusters that survive the size filter (cluster_table.cuh).
+template <int ITEMS>
 __global__ void __launch_bounds__(C1P_THREADS) k_compact_keys_onepass(const uint32_t* __restrict__ keys, int n, uint32_t drop, uint32_t* __restrict__ kout,
                                                                        uint32_t* __restrict__ vout, unsigned* status, int n_tiles,
                                                                        int* __restrict__ err_flag) {
+    static_assert(ITEMS % 4 == 0, "16-byte loads");
+    constexpr int TILE = C1P_THREADS * ITEMS;
     __shared__ int scratch[36];
     __shared__ int s_tile, s_base;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(status + n_tiles, 1u);
     __syncthreads();
     const int tile = s_tile;
     if (tile >= n_tiles) return;
-    const int i0 = tile * C1P_TILE + threadIdx.x * C1P_ITEMS;
-    uint32_t k[C1P_ITEMS];
+    const int i0 = tile * TILE + threadIdx.x * ITEMS;
+    uint32_t k[ITEMS];
     unsigned keepm = 0;
-    if (i0 + C1P_ITEMS <= n) {  // two 16-byte loads (i0 is a multiple of 8)
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i0)), b = __ldg(reinterpret_cast<const uint4*>(keys + i0) + 1);
-        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    if (i0 + ITEMS <= n) {  // 16-byte loads (i0 is a multiple of ITEMS)
 #pragma unroll
-        for (int j = 0; j < C1P_ITEMS; ++j) keepm |= (k[j] != drop ? 1u : 0u) << j;
+        for (int v = 0; v < ITEMS / 4; ++v) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i0) + v);
+            k[4 * v] = a.x; k[4 * v + 1] = a.y; k[4 * v + 2] = a.z; k[4 * v + 3] = a.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < C1P_ITEMS; ++j) {
-            k[j] = i0 + j < n ? keys[i0 + j] : drop;
-            keepm |= (k[j] != drop ? 1u : 0u) << j;
-        }
+        for (int j = 0; j < ITEMS; ++j) k[j] = i0 + j < n ? keys[i0 + j] : drop;
     }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) keepm |= (k[j] != drop ? 1u : 0u) << j;
     int tile_total;
     const int excl = block_exclusive_scan(__popc(keepm), scratch, &tile_total);
     if (threadIdx.x == 0) __stcg(status + tile, (tile == 0 ? C1P_INCL : C1P_AGG) | (unsigned)tile_total);
@@ -244,15 +247,23 @@ __global__ void __launch_bounds__(C1P_THREADS) k_compact_keys_onepass(const uint
         const int prefix = c1p_lookback(status, tile, tile_total, err_flag);
         if (lane_id() == 0) s_base = prefix;
     }
-    __syncthreads();
-    int w = s_base + excl;
+    // kept pairs go through shared memory so that the tile leaves as one coalesced run (written straight from the
+    // registers every lane of a store hits its own sector: 106 us for 16.8 M keys; staged: see profiles/r02_csr_compact.txt)
+    __shared__ uint32_t s_k[TILE], s_v[TILE];
+    int w = excl;
 #pragma unroll
-    for (int j = 0; j < C1P_ITEMS; ++j)
+    for (int j = 0; j < ITEMS; ++j)
         if ((keepm >> j) & 1u) {
-            kout[w] = k[j];
-            vout[w] = (uint32_t)(i0 + j);
+            s_k[w] = k[j];
+            s_v[w] = (uint32_t)(i0 + j);
             ++w;
         }
+    __syncthreads();
+    const int base = s_base;
+    for (int t = threadIdx.x; t < tile_total; t += C1P_THREADS) {
+        kout[base + t] = s_k[t];
+        vout[base + t] = s_v[t];
+    }
 }
 
 template <int MODE>

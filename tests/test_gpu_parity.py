@@ -231,7 +231,7 @@ def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
 
 ALTERNATIVES = [{"MOT_UF_MODE": "2"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0"},
                 {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1", "MOT_UF_PHASES": "7,24"}, {"MOT_UF_MODE": "2", "MOT_UF_FBLOCKS": "2"}, {"MOT_UF_MODE": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1024"},
-                {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0", "MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"}, {"MOT_KEYS_HIST": "1"}, {"MOT_CSR_COMPACT": "1"}, {"MOT_SORT_BIGTILE": "1000"},
+                {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0", "MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"}, {"MOT_KEYS_HIST": "1"}, {"MOT_CSR_COMPACT": "0"}, {"MOT_CSR_COMPACT": "8"}, {"MOT_SORT_BIGTILE": "1000"},
                 {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}]
 
 
