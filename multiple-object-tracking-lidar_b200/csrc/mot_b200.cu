@@ -1376,6 +1376,8 @@ static int batch_core(mot_handle* h, const float4* d_src, size_t total, int n_fr
         if (rc != MOT_OK) return rc;
         rc = cluster_core(h, h->d_pts, -1, n_frames, with_centroids != 0, 0.0);
     } else {
+        if (do_remove_static && n_frames > 1)  // nothing to compact: the kept cloud's frame boundaries are all zero
+            CK(cudaMemsetAsync(h->d_frame_offsets, 0, (size_t)(n_frames + 1) * sizeof(int), h->stream));
         rc = cluster_core(h, d_src, (int)total, n_frames, with_centroids != 0, 0.0);
     }
     return rc;

@@ -228,3 +228,25 @@ def test_c4_full_shape(mot, oracle, synth):
             assert np.array_equal(lab, ref), f"tol {tol}: labels"
             o_ref, i_ref = oracle.csr_from_labels(ref, p4["min_cluster_size"], p4["max_cluster_size"])
             assert np.array_equal(off, o_ref) and np.array_equal(idx, i_ref), f"tol {tol}: CSR"
+
+
+def test_frame_batch_edge_cases(mot, oracle, synth):
+    # everything removed by the map; empty frames first / last; a batch of only empty frames
+    occ, resn, origin = synth.make_map_c1()
+    p = synth.C1_PARAMS
+    cloud, _ = synth.make_frame_c1(n_points=8000)
+    t = mot.Tracker(device=0, max_points=1 << 16, max_tracks=0)
+    t.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    blocked = np.full_like(occ, 100)
+    t.set_map(blocked, resn, origin[:2], static_tolarance=0)
+    res = t.frame_batch([cloud, cloud[:100]], do_remove_static=True)
+    assert res["K"] == 0 and not res["frame_kept_offsets"].any() and not res["frame_cluster_offsets"].any() and len(res["indices"]) == 0
+    t.set_map(occ, resn, origin[:2], static_tolarance=p["static_tolerance"])
+    empty = np.zeros((0, 4), np.float32)
+    clouds = [empty, cloud, empty, empty, cloud[::2].copy(), empty]
+    res = t.frame_batch(clouds, do_remove_static=True, stamps=np.arange(6, dtype=np.float32))
+    _check_batch_against_oracle(res, clouds, oracle, occ, resn, origin, p, np.arange(6, dtype=np.float32))
+    assert res["frame_cluster_offsets"][1] == 0 and res["frame_cluster_offsets"][2] == res["frame_cluster_offsets"][4]
+    res = t.frame_batch([empty, empty], do_remove_static=True)
+    assert res["K"] == 0 and len(res["indices"]) == 0 and not res["frame_kept_offsets"].any()
+    t.close()
