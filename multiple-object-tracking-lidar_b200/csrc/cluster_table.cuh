@@ -225,18 +225,23 @@ __device__ __forceinline__ void stat_flush(StatAcc* acc, int cid, double s0, dou
 }
 
 constexpr int STAT_THREADS = 256;
-constexpr int STAT_GROUPS_PER_WARP = 16;  // 512 CSR entries per warp
+// 32-entry groups a warp walks: as many as it takes to give every SM ~16 warps, at most STAT_GROUPS_PER_WARP
+inline int stat_groups(long long total, int num_sms) {
+    long long g = total / (32ll * 16 * num_sms);
+    return (int)(g < 1 ? 1 : (g > 16 ? 16 : g));
+}
+constexpr int STAT_GROUPS_PER_WARP = 16;  // at most 512 CSR entries per warp; small tables use fewer (stat_groups) so that every SM gets warps
 __global__ void __launch_bounds__(STAT_THREADS) k_stats_accumulate(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
                                                                     const uint32_t* __restrict__ indices, int K, int total,
-                                                                    StatAcc* __restrict__ acc) {
+                                                                    StatAcc* __restrict__ acc, int groups = STAT_GROUPS_PER_WARP) {
     const int lane = lane_id();
     const int warp_global = blockIdx.x * (STAT_THREADS / 32) + warp_id();
-    const int t_begin = warp_global * (32 * STAT_GROUPS_PER_WARP);
+    const int t_begin = warp_global * (32 * groups);
     if (t_begin >= total) return;
     int cur = -1, cur_end = 0;  // warp-uniform: cluster whose points the lane accumulators currently hold
     double s0 = 0, s1 = 0, s2 = 0;
     float n0 = INFINITY, n1 = INFINITY, n2 = INFINITY, x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY;
-    for (int gidx = 0; gidx < STAT_GROUPS_PER_WARP; ++gidx) {
+    for (int gidx = 0; gidx < groups; ++gidx) {
         const int t0 = t_begin + gidx * 32;
         if (t0 >= total) break;
         const int t = t0 + lane;

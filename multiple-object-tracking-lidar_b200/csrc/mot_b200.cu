@@ -616,9 +616,10 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         if (rc != MOT_OK) return rc;
         int sgrid = K < h->num_sms * 16 ? K : h->num_sms * 16;
         LAUNCH(KID_STATS_INIT, k_stats_init<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, K));
-        const int per_block = 32 * STAT_GROUPS_PER_WARP * (STAT_THREADS / 32);
+        const int sg = stat_groups(total, h->num_sms);
+        const int per_block = 32 * sg * (STAT_THREADS / 32);
         LAUNCH(KID_STATS, k_stats_accumulate<<<(total + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf],
-                                                                                                         K, total, h->d_statacc));
+                                                                                                         K, total, h->d_statacc, sg));
         LAUNCH(KID_STATS_FIN, k_stats_finalize<<<(K + 255) / 256, 256, 0, st>>>(h->d_statacc, h->d_cl_offsets, K, h->d_stats));
         if (cent) {
             LAUNCH(KID_FARTHEST_PAIR, k_farthest_pair<<<K * slabs, FP_THREADS, 0, st>>>(cloud, h->d_cl_offsets, h->d_vals[h->res_idx_buf], K, slabs,
@@ -1059,8 +1060,9 @@ static int voxel_grid_device(mot_handle* h, const float4* d_src, int n, float lx
     int rc = ensure_tables(h, (size_t)V, 0);
     if (rc != MOT_OK) return rc;
     LAUNCH(KID_STATS_INIT, k_stats_init<<<(V + 255) / 256, 256, 0, st>>>(h->d_statacc, V));
-    const int per_block = 32 * STAT_GROUPS_PER_WARP * (STAT_THREADS / 32);
-    LAUNCH(KID_STATS, k_stats_accumulate<<<(n + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(d_src, h->d_cl_offsets, h->d_vals[sb], V, n, h->d_statacc));
+    const int sg = stat_groups(n, h->num_sms);
+    const int per_block = 32 * sg * (STAT_THREADS / 32);
+    LAUNCH(KID_STATS, k_stats_accumulate<<<(n + per_block - 1) / per_block, STAT_THREADS, 0, st>>>(d_src, h->d_cl_offsets, h->d_vals[sb], V, n, h->d_statacc, sg));
     LAUNCH(KID_VOX_FIN, k_voxel_finalize<<<(V + 255) / 256, 256, 0, st>>>(h->d_statacc, h->d_cl_offsets, V, h->d_pts));
     CK(cudaGetLastError());
     *m_out = V;
@@ -1755,13 +1757,14 @@ static int ihgp_step_impl(mot_handle* h, const float* rings, int n_tracks, const
     CK(cudaMemcpyAsync(h->d_rings, rings, ring_elems * 16, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->d_mstate, m_state, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (obstacles && ids) CK(cudaMemcpyAsync(h->d_track_ids, ids, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
+    const int epw = ihgp_entries_per_warp(L, 112 * 1024, n_tracks, h->num_sms);
+    const size_t smem = ihgp_smem_bytes(L, epw);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (n_tracks + IHGP_WARPS - 1) / IHGP_WARPS;
+    int grid = ((n_tracks + epw - 1) / epw + IHGP_WARPS - 1) / IHGP_WARPS;
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_rings, n_tracks, L, (float)h->ihgp_dt, h->ihgp_tau, h->ihgp_axis[0],
                                                                       h->ihgp_axis[1], h->d_mstate, h->d_posvel, (obstacles && ids) ? h->d_track_ids : nullptr,
-                                                                      obstacles ? h->d_obstacles : nullptr, nullptr, nullptr, 0));
+                                                                      obstacles ? h->d_obstacles : nullptr, nullptr, nullptr, 0, epw));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(m_state, h->d_mstate, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)n_tracks * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1836,14 +1839,15 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
         CK(cudaMemsetAsync(h->d_posvel, 0, (size_t)K * 2 * sizeof(float4), st));
         CK(cudaMemsetAsync(h->d_obstacles, 0, (size_t)K * sizeof(ObstacleRow), st));
     }
-    const size_t smem = (size_t)IHGP_WARPS * (L - 1) * 6 * sizeof(double);
+    const int epw = ihgp_entries_per_warp(L, 112 * 1024, K, h->num_sms);
+    const size_t smem = ihgp_smem_bytes(L, epw);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_ihgp_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (K + IHGP_WARPS - 1) / IHGP_WARPS;
+    int grid = ((K + epw - 1) / epw + IHGP_WARPS - 1) / IHGP_WARPS;
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     for (int r = 0; r <= max_occ; ++r)
         LAUNCH(KID_IHGP, k_ihgp_step<<<grid, IHGP_WARPS * 32, smem, st>>>(h->d_trk_rings[cur], K, L, dt_gp, h->ihgp_tau, h->ihgp_axis[0], h->ihgp_axis[1],
                                                                           h->d_trk_m[cur], h->d_posvel, h->d_ent_ids, h->d_obstacles, h->d_ent_slot,
-                                                                          h->d_ent_occ, r));
+                                                                          h->d_ent_occ, r, epw));
     if (pos_vel) CK(cudaMemcpyAsync(pos_vel, h->d_posvel, (size_t)K * 8 * sizeof(float), cudaMemcpyDefault, st));
     if (obstacles) CK(cudaMemcpyAsync(obstacles, h->d_obstacles, (size_t)K * sizeof(ObstacleRow), cudaMemcpyDefault, st));
     // unregisterOldObstacle (MOT.cpp:545-584)
