@@ -115,6 +115,7 @@ def kernel_bytes(name, M, cf, cc, K, total, key_bytes, n_sort_passes, R_G=1024 *
         "k_coarse_records": 12 * cf + 80 * cc,            # record (16 B) + neighbour row (64 B) per coarse cell
         "k_uf_sparse": 16 * M + 80 * cc + 8 * cf,         # every sorted point once + record/neighbour row + parent r/w
         "k_uf_sparse2": 16 * M + 80 * cc + 8 * cf,        # same traffic, half a warp per coarse cell
+        "k_hash_build": 4 * cc + 16 * cc,                    # coarse key in, one hash slot (key + value, <= 50 % load) out
         "k_cell_local": 16 * M + 41 * cf + 56 * cc,         # every sorted point once; cell tables in, boxes / records / parents out
         "k_uf_fused": 36 * cc + 40 * cf,                    # keys, records, hash, boxes, parents (points only for ambiguous pairs)
         "k_uf_cross": 68 * cc + 40 * cf,
@@ -401,7 +402,7 @@ def run_b200(args, rank, world, local_rank):
     k15 = ("k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count", "k_hash_clear", "k_cells_write",
            "k_coarse_records", "k_uf_sparse", "k_uf_sparse2", "k_uf_dense<1>", "k_uf_dense<2>", "k_uf_flatten<in-place>", "k_uf_flatten<root>",
            "k_uf_pairs<1>", "k_uf_pairs<2>", "k_cell_local", "k_uf_fused", "k_uf_cross", "k_uf_survivors", "k_uf_walk", "k_uf_heavy<1>",
-           "k_uf_heavy<2>", "k_uf_flatten_if")
+           "k_uf_heavy<2>", "k_uf_flatten_if", "k_cell_local_dense", "k_hash_build")
     t15_us = sum(v[0] for kname, v in prof.items() if kname in k15) / prof_steps * 1e3
     b15 = (104 + 16 * P) * M + 16 * grid["coarse_cells"]
     grid_uf = {"alg_bytes_per_step": b15, "kernel_us_per_step": round(t15_us, 1), "gbs": round(b15 / (t15_us * 1e-6) / 1e9, 1),

@@ -237,19 +237,34 @@ __device__ __forceinline__ void cloc_finish(ClocWarpSmem& sm, int lane, bool val
     }
     cbox[2 * (size_t)ci] = make_float4(c_mn0, c_mn1, c_mn2, 0.0f);
     cbox[2 * (size_t)ci + 1] = make_float4(c_mx0, c_mx1, c_mx2, 0.0f);
-    // connected components among the children (all of them are ring-1 neighbours of each other)
+    // connected components among the children (all of them are ring-1 neighbours of each other).  Pass 1 merges what the boxes
+    // alone prove (no point is read); pass 2 decides the pairs that are still in different components -- most ambiguous pairs
+    // have been connected through a third child by then and never reach the witness search.
     unsigned lab = 0x76543210u;  // 4 bits per child rank: smallest rank of its component
-    for (int i = 0; i < n_a - 1; ++i) {
-        const float4 alo = lo_of(l0 + i), ahi = hi_of(l0 + i);
-        for (int j = i + 1; j < n_a; ++j) {
-            const unsigned li = (lab >> (4 * i)) & 15u, lj = (lab >> (4 * j)) & 15u;
-            if (li == lj) continue;
-            UFSTAT(ST_LOCAL_PAIRS, 1);
-            const float4 blo = lo_of(l0 + j), bhi = hi_of(l0 + j);
-            if (!fine_pair(spts, alo, ahi, blo, bhi, f0 + i, f0 + j, 1, r2, light, heavy1, heavy2, heavy_cap, d_counts)) continue;
-            const unsigned lo = min(li, lj), hi = max(li, lj);
-            for (int k = 0; k < n_a; ++k)
-                if (((lab >> (4 * k)) & 15u) == hi) lab = (lab & ~(15u << (4 * k))) | (lo << (4 * k));
+    auto relabel = [&](unsigned hi, unsigned lo) {  // every nibble equal to hi becomes lo (nibble-parallel)
+        const unsigned x = lab ^ (hi * 0x11111111u);
+        const unsigned nz = (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u;  // bit 3 of a nibble set <=> nibble != 0
+        const unsigned sel = ((~nz & 0x88888888u) >> 3) * 15u;                          // 0xF where the nibble was hi
+        lab = (lab & ~sel) | ((lo * 0x11111111u) & sel);
+    };
+    for (int pass = 0; pass < 2 && n_a >= 2; ++pass) {
+        for (int i = 0; i < n_a - 1; ++i) {
+            const float4 alo = lo_of(l0 + i), ahi = hi_of(l0 + i);
+            for (int j = i + 1; j < n_a; ++j) {
+                const unsigned li = (lab >> (4 * i)) & 15u, lj = (lab >> (4 * j)) & 15u;
+                if (li == lj) continue;
+                const float4 blo = lo_of(l0 + j), bhi = hi_of(l0 + j);
+                bool hit;
+                if (pass == 0) {
+                    float lower, upper;
+                    box_bounds(alo, ahi, blo, bhi, lower, upper);
+                    hit = upper < r2;
+                } else {
+                    UFSTAT(ST_LOCAL_PAIRS, 1);
+                    hit = fine_pair(spts, alo, ahi, blo, bhi, f0 + i, f0 + j, 1, r2, light, heavy1, heavy2, heavy_cap, d_counts);
+                }
+                if (hit) relabel(max(li, lj), min(li, lj));
+            }
         }
     }
     unsigned lab3 = 0;

@@ -194,60 +194,77 @@ __global__ void __launch_bounds__(256) k_hash_clear(const int* __restrict__ coun
 // d_counts layout (ints): [0] fine cells, [1] coarse cells, [2] kept clusters, [3] kept points, [4] flags
 
 
+constexpr int CELLW_ITEMS = 4;  // consecutive sorted positions per thread: one block scan per 1024 points, four gathers in flight
+constexpr int CELLW_TILE = CELL_THREADS * CELLW_ITEMS;
+
 template <typename KT>
 __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restrict__ skeys, const uint32_t* __restrict__ svals,
                                                                const float4* __restrict__ pts, float4* __restrict__ spts, int m,
                                                                int chunk, const int* __restrict__ counts, int* __restrict__ fc_start,
                                                                int* __restrict__ cc_first,
                                                                int* __restrict__ parent, int* __restrict__ csize, int* __restrict__ cmin,
-                                                               int* __restrict__ crank, KT* __restrict__ hkeys, int* __restrict__ hvals,
-                                                               unsigned hmask, int hshift, int* __restrict__ d_counts,
-                                                               KT* __restrict__ ckey_out /* sorted coarse keys (cell_uf.cuh), may be null */,
+                                                               int* __restrict__ crank, int* __restrict__ d_counts,
+                                                               KT* __restrict__ ckey_out /* sorted coarse keys */,
                                                                unsigned char* __restrict__ fcode_out /* child code of every fine cell, may be null */) {
     __shared__ int scratch[36];
-    {
-        const int hb = d_counts[CNT_HB];  // set by k_hash_clear
-        hmask = (1u << hb) - 1u;
-        hshift = 32 - hb;
-    }
     int fbase = counts[2 * gridDim.x + blockIdx.x];  // exclusive prefixes written by k_hash_clear behind the two count rows
     int cbase = counts[3 * gridDim.x + blockIdx.x];
     const int begin = blockIdx.x * chunk, end = min(m, begin + chunk);
-    for (int tb = begin; tb < end; tb += CELL_THREADS) {
-        const int j = tb + threadIdx.x;
-        int fh = 0, ch = 0;
-        KT k = 0;
-        if (j < end) {
-            k = skeys[j];
-            if (j == 0) { fh = 1; ch = 1; }
-            else {
-                const KT kp = skeys[j - 1];
-                fh = (k != kp);
-                ch = ((k >> 3) != (kp >> 3));
+    for (int tb = begin; tb < end; tb += CELLW_TILE) {
+        const int j0 = tb + threadIdx.x * CELLW_ITEMS;
+        KT k[CELLW_ITEMS];
+        uint32_t sv[CELLW_ITEMS];
+        float4 p[CELLW_ITEMS];
+        unsigned fh = 0, ch = 0;  // bit i: position j0 + i starts a fine / coarse cell
+        KT kp = 0;
+        if (j0 > 0 && j0 < end) kp = skeys[j0 - 1];
+#pragma unroll
+        for (int i = 0; i < CELLW_ITEMS; ++i) {
+            const int j = j0 + i;
+            k[i] = 0;
+            sv[i] = 0;
+            if (j < end) {
+                k[i] = skeys[j];
+                sv[i] = svals[j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CELLW_ITEMS; ++i)
+            if (j0 + i < end) p[i] = pts[sv[i]];  // the random 16-byte gathers of the tile, all in flight before the scan's barriers
+#pragma unroll
+        for (int i = 0; i < CELLW_ITEMS; ++i) {
+            const int j = j0 + i;
+            if (j < end) {
+                const KT prev = i == 0 ? kp : k[i - 1];
+                if (j == 0 || k[i] != prev) fh |= 1u << i;
+                if (j == 0 || (k[i] >> 3) != (prev >> 3)) ch |= 1u << i;
             }
         }
         int total;
-        const int packed = (ch << 16) | fh;
-        const int excl = block_exclusive_scan(packed, scratch, &total);
-        const int fi = fbase + (excl & 0xffff) + fh - 1;  // index of the fine cell containing j
-        if (j < end) {
+        const int excl = block_exclusive_scan((__popc(ch) << 16) | __popc(fh), scratch, &total);
+        int f_run = fbase + (excl & 0xffff), c_run = cbase + (excl >> 16);
+#pragma unroll
+        for (int i = 0; i < CELLW_ITEMS; ++i) {
+            const int j = j0 + i;
+            if (j >= end) break;
+            const bool is_fh = (fh >> i) & 1u, is_ch = (ch >> i) & 1u;
+            f_run += is_fh;
+            const int fi = f_run - 1;  // index of the fine cell containing j
             // sorted SoA point: (x, y, z, bits(fine cell id)) -- the union-find kernels get a point's cell for free
-            float4 p = pts[svals[j]];
-            p.w = __int_as_float(fi);
-            spts[j] = p;
-            if (fh) {
+            p[i].w = __int_as_float(fi);
+            spts[j] = p[i];
+            if (is_fh) {
                 fc_start[fi] = j;
                 parent[fi] = fi;
                 csize[fi] = 0;
-                cmin[fi] = (int)svals[j];  // stable sort: the first point of a cell has its smallest original index
+                cmin[fi] = (int)sv[i];  // stable sort: the first point of a cell has its smallest original index
                 crank[fi] = -1;
-                if (fcode_out) fcode_out[fi] = (unsigned char)(k & 7);
+                if (fcode_out) fcode_out[fi] = (unsigned char)(k[i] & 7);
             }
-            if (ch) {
-                const int ci = cbase + (excl >> 16);
-                cc_first[ci] = fi;
-                if (ckey_out) ckey_out[ci] = k >> 3;
-                hash_insert<KT>(hkeys, hvals, hmask, hshift, k >> 3, ci);
+            if (is_ch) {
+                cc_first[c_run] = fi;
+                ckey_out[c_run] = k[i] >> 3;
+                ++c_run;
             }
         }
         fbase += total & 0xffff;
@@ -259,6 +276,19 @@ __global__ void __launch_bounds__(CELL_THREADS) k_cells_write(const KT* __restri
         d_counts[CNT_FINE] = fbase;
         d_counts[CNT_COARSE] = cbase;
     }
+}
+
+// coarse key -> coarse cell index.  One thread per coarse cell: in k_cells_write the insert was done by the one lane in ~10 that
+// starts a coarse cell while the other lanes of the warp waited for its compare-and-swap (27 % of that kernel's stall samples).
+template <typename KT>
+__global__ void __launch_bounds__(256) k_hash_build(const KT* __restrict__ ckey, const int* __restrict__ d_counts, KT* __restrict__ hkeys,
+                                                     int* __restrict__ hvals) {
+    const int n_coarse = d_counts[CNT_COARSE];
+    const int hb = d_counts[CNT_HB];
+    const unsigned hmask = (1u << hb) - 1u;
+    const int hshift = 32 - hb;
+    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_coarse; ci += gridDim.x * blockDim.x)
+        hash_insert<KT>(hkeys, hvals, hmask, hshift, ckey[ci], ci);
 }
 
 // ---- union-find primitives (parents only ever decrease; atomicMin hooking + path halving) --------------

@@ -52,7 +52,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -60,7 +60,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build"};
 
 struct mot_handle {
     int device = 0;
@@ -343,14 +343,20 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     while (((size_t)1 << hb_max) > h->hash_capacity) --hb_max;  // capacity holds >= 2 slots per point: load <= 0.5 always
     const unsigned hmask = 0;  // both are read from d_counts[CNT_HB] inside the kernels
     const int hshift = 0;
-    const Chunking ck = make_chunking(M, CELL_THREADS, CELLW_MAX_GRID);
+    const Chunking ck = make_chunking(M, CELLW_TILE, CELLW_MAX_GRID);
     LAUNCH(KID_CELLS_COUNT, k_cells_count<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, M, ck.chunk, h->d_blk));
     LAUNCH(KID_HASH_CLEAR, k_hash_clear<KT><<<h->num_sms * 2, 256, 0, st>>>(h->d_blk, ck.grid, hb_max, reinterpret_cast<KT*>(h->d_hkeys), h->d_counts,
                                                                              h->d_blk + 2 * ck.grid));
     LAUNCH(KID_CELLS_WRITE, k_cells_write<KT><<<ck.grid, CELL_THREADS, 0, st>>>(skeys, svals, cloud, h->d_spts, M, ck.chunk, h->d_blk, h->d_fc_start,
                                                                                h->d_cc_first, h->d_parent, h->d_csize, h->d_cmin, h->d_crank,
-                                                                               reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals, hmask, hshift,
-                                                                               h->d_counts, h->uf_mode_now == 2 ? reinterpret_cast<KT*>(h->d_ckey) : nullptr, h->uf_mode_now == 2 ? h->d_fcode : nullptr));
+                                                                               h->d_counts, reinterpret_cast<KT*>(h->d_ckey),
+                                                                               h->uf_mode_now == 2 ? h->d_fcode : nullptr));
+    {
+        int hgrid = (M + 255) / 256;
+        if (hgrid > h->num_sms * 8) hgrid = h->num_sms * 8;
+        LAUNCH(KID_HASH_BUILD, k_hash_build<KT><<<hgrid, 256, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_counts,
+                                                                        reinterpret_cast<KT*>(h->d_hkeys), h->d_hvals));
+    }
     CK(cudaEventRecord(h->ev[2], st));
 
     const float r2 = (float)((double)h->tol * (double)h->tol);  // KdTreeFLANN::radiusSearch: (float)(radius*radius)
