@@ -843,13 +843,15 @@ struct WalkLane {          // one cell pair being walked, packed (lives in regis
     unsigned misc;         // bit 0 live, 1 single, 2-3 dx+1, 4-5 dy+1, 6-7 dz+1, 8-10 code of the current child, 11-13 its rank
 };
 
-__device__ __forceinline__ void walk_load(WalkLane& w, const int4* __restrict__ crec, const int4& tk) {
-    const int4 ra = __ldg(crec + tk.x), rb = __ldg(crec + tk.y);
+// queue entry: x = A | code << 27 (code = dx+1 | row << 2), y = B -- 8 bytes, so that ten resident CTAs leave the L1 alone
+__device__ __forceinline__ void walk_load(WalkLane& w, const int4* __restrict__ crec, const int2& tk) {
+    const int code = (int)((unsigned)tk.x >> 27), row = code >> 2;
+    const int4 ra = __ldg(crec + (tk.x & 0x7ffffff)), rb = __ldg(crec + tk.y);
     w.f0A = ra.z; w.f0B = rb.z;
     const unsigned mA = (unsigned)ra.w & 0xffu, mB = (unsigned)rb.w & 0xffu;
     w.labA = (unsigned)ra.w >> 8; w.labB = (unsigned)rb.w >> 8;
     w.masks = mA | (mB << 8) | (mA << 16);
-    w.misc = 1u | ((w.labA | w.labB) == 0u ? 2u : 0u) | ((unsigned)tk.z << 2);
+    w.misc = 1u | ((w.labA | w.labB) == 0u ? 2u : 0u) | ((unsigned)((code & 3) | ((c_row_dy[row] + 1) << 2) | ((c_row_dz[row] + 1) << 4)) << 2);
 }
 
 // one step of a live lane: advance to the next candidate fine pair and decide it
@@ -923,8 +925,8 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
                                                                            int* __restrict__ d_counts, int* parent, GridCodec g, float r2, int light,
                                                                            int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap,
                                                                            int row_inner) {
-    __shared__ int4 s_queue[UFF_WARPS][UFF_QUEUE];
-    int4* q = s_queue[warp_id()];
+    __shared__ int2 s_queue[UFF_WARPS][UFF_QUEUE];
+    int2* q = s_queue[warp_id()];
     int qn = 0;  // warp uniform
     WalkLane w{0, 0, 0u, 0u, 0u, 0u};
     const int lane = lane_id();
@@ -943,7 +945,7 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
             const int k = __popc(idle & lanemask_lt());
             MOT_CHECK(qn >= 0 && qn <= UFF_QUEUE, d_counts);
             if (!(w.misc & 1u) && k < take) {
-                MOT_CHECK(q[qn - 1 - k].x >= 0 && q[qn - 1 - k].x < n_coarse && q[qn - 1 - k].y >= 0 && q[qn - 1 - k].y < n_coarse, d_counts);
+                MOT_CHECK((q[qn - 1 - k].x & 0x7ffffff) < n_coarse && q[qn - 1 - k].y >= 0 && q[qn - 1 - k].y < n_coarse, d_counts);
                 walk_load(w, crec, q[qn - 1 - k]);
             }
             qn -= take;
@@ -1027,10 +1029,9 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
             const int mine = __popc(keep);
             const int incl = warp_inclusive_scan(mine);
             int slot = qn + incl - mine;
-            const int dcode = ((dy + 1) << 2) | ((dz + 1) << 4);
-            if (keep & 1u) q[slot++] = make_int4(A, nb0, 1 | dcode, 0);
-            if (keep & 2u) q[slot++] = make_int4(A, nb1, 0 | dcode, 0);
-            if (keep & 4u) q[slot++] = make_int4(A, nb2, 2 | dcode, 0);
+            if (keep & 1u) q[slot++] = make_int2((int)((unsigned)A | ((unsigned)(1 | (row << 2)) << 27)), nb0);
+            if (keep & 2u) q[slot++] = make_int2((int)((unsigned)A | ((unsigned)(0 | (row << 2)) << 27)), nb1);
+            if (keep & 4u) q[slot++] = make_int2((int)((unsigned)A | ((unsigned)(2 | (row << 2)) << 27)), nb2);
             qn += __shfl_sync(kFull, incl, 31);
             MOT_CHECK(qn <= UFF_QUEUE, d_counts);
             __syncwarp();

@@ -132,6 +132,8 @@ struct mot_handle {
     float4 *d_cbox = nullptr, *d_fbox = nullptr;  // AABB of every coarse / fine cell (2 x float4 each)
     int2 *d_heavy1 = nullptr, *d_heavy2 = nullptr;
     int heavy_cap = 0;
+    int l2_persist_mb = 0;  // MOT_L2_PERSIST: MB of L2 set aside (persisting access window) for parent[] / the coarse records during the union-find kernels
+    int l2_persist_what = 0; // MOT_L2_WHAT: 0 = parent[], 1 = coarse records
     int uf_row_inner = 0;   // MOT_UF_ROWINNER: k_uf_fused item order (see the kernel)
     int cell_dense = 1;     // batches of > 2048 points go to k_cell_local_dense (MOT_CELL_DENSE=0: one warp walks any batch)
     int uf_light = 256;     // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
@@ -371,6 +373,15 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             CK(cudaEventRecord(h->ev_uf[0], main_st));
             CK(cudaStreamWaitEvent(h->uf_stream, h->ev_uf[0], 0));
             st = h->uf_stream;
+        }
+        if (h->l2_persist_mb > 0) {  // keep the randomly accessed table of the walk resident in L2 across the five row sweeps
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = h->l2_persist_what == 0 ? (void*)h->d_parent : (void*)h->d_crec;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)M * (h->l2_persist_what == 0 ? 1 : 2), (size_t)h->l2_persist_mb << 20);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
         }
         int lgrid = (M + CLOC_THREADS - 1) / CLOC_THREADS;
         if (lgrid > h->num_sms * 7) lgrid = h->num_sms * 7;
@@ -804,6 +815,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->heavy_cap = (int)(n / 2 + 4096);
         CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
         CK(dalloc(&h->d_heavy2, (size_t)h->heavy_cap));
+        if (const char* e = getenv("MOT_L2_PERSIST")) h->l2_persist_mb = std::max(0, atoi(e));
+        if (const char* e = getenv("MOT_L2_WHAT")) h->l2_persist_what = atoi(e);
+        if (h->l2_persist_mb > 0) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)h->l2_persist_mb << 20));
         if (const char* e = getenv("MOT_UF_ROWINNER")) h->uf_row_inner = atoi(e);
         if (const char* e = getenv("MOT_CELL_DENSE")) h->cell_dense = atoi(e);
         if (const char* e = getenv("MOT_UF_AUTO")) h->uf_auto_points = std::max(0, atoi(e));
