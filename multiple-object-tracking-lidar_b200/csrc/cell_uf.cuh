@@ -235,8 +235,10 @@ __device__ __forceinline__ void cloc_finish(ClocWarpSmem& sm, int lane, bool val
         c_mn0 = fminf(c_mn0, sm.mn[0][x]); c_mn1 = fminf(c_mn1, sm.mn[1][x]); c_mn2 = fminf(c_mn2, sm.mn[2][x]);
         c_mx0 = fmaxf(c_mx0, sm.mx[0][x]); c_mx1 = fmaxf(c_mx1, sm.mx[1][x]); c_mx2 = fmaxf(c_mx2, sm.mx[2][x]);
     }
-    cbox[2 * (size_t)ci] = make_float4(c_mn0, c_mn1, c_mn2, 0.0f);
-    cbox[2 * (size_t)ci + 1] = make_float4(c_mx0, c_mx1, c_mx2, 0.0f);
+    if (cbox) {  // only the lock-step variant k_uf_cross rejects cell pairs from the coarse boxes
+        cbox[2 * (size_t)ci] = make_float4(c_mn0, c_mn1, c_mn2, 0.0f);
+        cbox[2 * (size_t)ci + 1] = make_float4(c_mx0, c_mx1, c_mx2, 0.0f);
+    }
     // connected components among the children (all of them are ring-1 neighbours of each other).  Pass 1 merges what the boxes
     // alone prove (no point is read); pass 2 decides the pairs that are still in different components -- most ambiguous pairs
     // have been connected through a third child by then and never reach the witness search.

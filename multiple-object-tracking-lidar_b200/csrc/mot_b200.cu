@@ -387,13 +387,13 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
         if (lgrid > h->num_sms * 7) lgrid = h->num_sms * 7;
         int* dlist = h->cell_dense ? h->d_dense_list : nullptr;
         LAUNCH(KID_CELL_LOCAL, k_cell_local<<<lgrid, CLOC_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2, h->uf_light,
-                                                                           h->d_crec, h->d_cbox, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
+                                                                           h->d_crec, h->uf_xmode == 0 ? h->d_cbox : nullptr, h->d_fbox, h->d_parent, h->d_heavy1, h->d_heavy2,
                                                                            h->heavy_cap, dlist, h->dense_cap));
         if (dlist) {
             int dgrid = (M + CLOC_DENSE_POINTS - 1) / CLOC_DENSE_POINTS;
             if (dgrid > h->num_sms * 3) dgrid = h->num_sms * 3;
             LAUNCH(KID_CELL_LOCAL_DENSE, k_cell_local_dense<<<dgrid, CLD_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2,
-                                                                                         h->uf_light, h->d_crec, h->d_cbox, h->d_fbox, h->d_parent,
+                                                                                         h->uf_light, h->d_crec, h->uf_xmode == 0 ? h->d_cbox : nullptr, h->d_fbox, h->d_parent,
                                                                                          h->d_heavy1, h->d_heavy2, h->heavy_cap, h->d_dense_list,
                                                                                          h->dense_cap));
         }
@@ -810,7 +810,8 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_nbr, n * 16));
         CK(cudaMalloc(&h->d_ckey, (n + 1) * 8 + 256));
         CK(dalloc(&h->d_fcode, n));
-        CK(dalloc(&h->d_cbox, 2 * n));
+        if (const char* e = getenv("MOT_UF_XMODE")) h->uf_xmode = atoi(e);
+        if (h->uf_xmode == 0) CK(dalloc(&h->d_cbox, 2 * n));  // the A/B variants' tables are only allocated when selected
         CK(dalloc(&h->d_fbox, 2 * n));
         h->heavy_cap = (int)(n / 2 + 4096);
         CK(dalloc(&h->d_heavy1, (size_t)h->heavy_cap));
@@ -851,7 +852,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
             }
             h->task_cap = (int)std::min<size_t>((size_t)worst * n + 64, 0x7ffffff0ull);
         }
-        CK(dalloc(&h->d_tasks, (size_t)h->task_cap));
+        if (h->uf_xmode == 1) CK(dalloc(&h->d_tasks, (size_t)h->task_cap));
         int hb = ceil_log2(2 * (long long)n);
         if (hb < 4) hb = 4;
         h->hash_capacity = (size_t)1 << hb;
