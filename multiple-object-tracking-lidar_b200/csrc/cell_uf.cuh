@@ -396,15 +396,15 @@ __global__ void __launch_bounds__(CLD_THREADS) k_cell_local_dense(const float4* 
         }
         __syncthreads();
         const int F0 = s_f[0], F1 = s_f[1], nf = F1 - F0;
-        for (int x = threadIdx.x; x < nf; x += CLD_THREADS) {
+        for (int x = threadIdx.x; x < nf; x += blockDim.x) {
             imn[0][x] = 0x7fffffff; imn[1][x] = 0x7fffffff; imn[2][x] = 0x7fffffff;
             imx[0][x] = (int)0x80000000; imx[1][x] = (int)0x80000000; imx[2][x] = (int)0x80000000;
             sm.code[x] = fcode[F0 + x];
         }
-        for (int x = threadIdx.x; x <= nf; x += CLD_THREADS) sm.start[x] = __ldg(fc_start + F0 + x);
+        for (int x = threadIdx.x; x <= nf; x += blockDim.x) sm.start[x] = __ldg(fc_start + F0 + x);
         __syncthreads();
         const int P0 = sm.start[0], P1 = sm.start[nf];
-        for (int jb = P0 + warp_id() * 32; jb < P1; jb += CLD_THREADS) {  // every warp: its 32-point groups, stride = CTA
+        for (int jb = P0 + warp_id() * 32; jb < P1; jb += blockDim.x) {  // every warp: its 32-point groups, stride = CTA
             const int j = jb + lane;
             const float4 p = j < P1 ? ld_stream(spts + j) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
             const int lf = __float_as_int(p.w) - F0;
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(CLD_THREADS) k_cell_local_dense(const float4* 
             }
         }
         __syncthreads();
-        for (int x = threadIdx.x; x < nf; x += CLD_THREADS) {
+        for (int x = threadIdx.x; x < nf; x += blockDim.x) {
             sm.mn[0][x] = ordered_to_float_bits(imn[0][x]); sm.mn[1][x] = ordered_to_float_bits(imn[1][x]); sm.mn[2][x] = ordered_to_float_bits(imn[2][x]);
             sm.mx[0][x] = ordered_to_float_bits(imx[0][x]); sm.mx[1][x] = ordered_to_float_bits(imx[1][x]); sm.mx[2][x] = ordered_to_float_bits(imx[2][x]);
         }
@@ -926,7 +926,7 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
                                                                            const KT* __restrict__ hkeys, const int* __restrict__ hvals,
                                                                            int* __restrict__ d_counts, int* parent, GridCodec g, float r2, int light,
                                                                            int2* __restrict__ heavy1, int2* __restrict__ heavy2, int heavy_cap,
-                                                                           int row_inner) {
+                                                                           int row_inner, int tile_batches) {
     __shared__ int2 s_queue[UFF_WARPS][UFF_QUEUE];
     int2* q = s_queue[warp_id()];
     int qn = 0;  // warp uniform
@@ -959,13 +959,28 @@ __global__ void __launch_bounds__(UFF_THREADS, UFF_MIN_BLOCKS) k_uf_fused(const 
     // work items = (neighbour row, batch of 32 cells), row-major: faces first, and a warp of a small launch gets its share of
     // ALL rows instead of walking the five rows one after the other (that serial chain was the single-frame latency)
     const int n_batches = (n_coarse + 31) >> 5;
-    for (long long item = blockIdx.x * UFF_WARPS + warp_id(); item < 5ll * n_batches; item += n_warps) {
-        // row_inner = 0: row-major (all cells for the face rows first: most root skips, but five sweeps over the cell tables);
-        // 1: the five rows of a batch of cells one after the other (one sweep: the tables of a batch stay in L1 / L2)
-        const int row = row_inner ? (int)(item % 5) : (int)(item / n_batches);
+    // Item order: tiles of `tile_batches` batches of cells; inside a tile row-major (all cells of the tile for the face rows
+    // first, which is what makes the root skips work).  A tile's tables (keys, records, hash slots, parents: ~60 B per cell)
+    // stay in L2 across its five row sweeps; with one tile = everything (tile_batches = 0) every sweep streams them from DRAM
+    // once the batch is larger than L2.  Frames never share components, so nothing is lost across tile borders but a few
+    // root skips at the seam.
+    const int tb = tile_batches > 0 ? min(tile_batches, n_batches) : n_batches;
+    const int n_tiles = tb > 0 ? (n_batches + tb - 1) / tb : 0;
+    for (long long item = blockIdx.x * UFF_WARPS + warp_id(); item < 5ll * tb * n_tiles; item += n_warps) {
+        int row, batch;
+        if (row_inner) {
+            row = (int)(item % 5);
+            batch = (int)(item / 5);
+        } else {
+            const int tile = (int)(item / (5ll * tb));
+            const int r = (int)(item - (long long)tile * 5 * tb);
+            row = r / tb;
+            batch = tile * tb + (r - row * tb);
+        }
+        if (batch >= n_batches) continue;  // warp uniform
         const int dy = c_row_dy[row], dz = c_row_dz[row];
         {
-            const int base = (row_inner ? (int)(item / 5) : (int)(item - (long long)row * n_batches)) * 32;
+            const int base = batch * 32;
             const int A = base + lane;
             int nb0 = -1, nb1 = -1, nb2 = -1;  // neighbour cells of this row at dx = 0, -1, +1 (centre first: it is the face neighbour)
             if (A < n_coarse) {

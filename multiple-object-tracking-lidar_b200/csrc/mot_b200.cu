@@ -134,7 +134,9 @@ struct mot_handle {
     int heavy_cap = 0;
     int l2_persist_mb = 0;  // MOT_L2_PERSIST: MB of L2 set aside (persisting access window) for parent[] / the coarse records during the union-find kernels
     int l2_persist_what = 0; // MOT_L2_WHAT: 0 = parent[], 1 = coarse records
+    int uf_tile_batches = 0;  // MOT_UF_TILE: k_uf_fused walks the cells in tiles of this many 32-cell batches (0 = one tile)
     int uf_row_inner = 0;   // MOT_UF_ROWINNER: k_uf_fused item order (see the kernel)
+    int cld_threads = 256;  // CTA width of k_cell_local_dense (MOT_CLD_THREADS: 128 / 256 / 512)
     int cell_dense = 1;     // batches of > 2048 points go to k_cell_local_dense (MOT_CELL_DENSE=0: one warp walks any batch)
     int uf_light = 256;     // fine-cell pairs with at most this many point pairs are searched by one thread (MOT_UF_LIGHT)
     int uf_cross_blocks = 4;  // resident CTAs of k_uf_cross per SM (MOT_UF_XBLOCKS)
@@ -391,8 +393,9 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
                                                                            h->heavy_cap, dlist, h->dense_cap));
         if (dlist) {
             int dgrid = (M + CLOC_DENSE_POINTS - 1) / CLOC_DENSE_POINTS;
-            if (dgrid > h->num_sms * 3) dgrid = h->num_sms * 3;
-            LAUNCH(KID_CELL_LOCAL_DENSE, k_cell_local_dense<<<dgrid, CLD_THREADS, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2,
+            const int per_sm = 1536 / h->cld_threads;
+            if (dgrid > h->num_sms * per_sm) dgrid = h->num_sms * per_sm;
+            LAUNCH(KID_CELL_LOCAL_DENSE, k_cell_local_dense<<<dgrid, h->cld_threads, 0, st>>>(h->d_spts, h->d_fc_start, h->d_cc_first, h->d_fcode, h->d_counts, r2,
                                                                                          h->uf_light, h->d_crec, h->uf_xmode == 0 ? h->d_cbox : nullptr, h->d_fbox, h->d_parent,
                                                                                          h->d_heavy1, h->d_heavy2, h->heavy_cap, h->d_dense_list,
                                                                                          h->dense_cap));
@@ -402,7 +405,7 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
             if (fgrid > h->num_sms * h->uf_fused_blocks) fgrid = h->num_sms * h->uf_fused_blocks;
             LAUNCH(KID_UF_FUSED, k_uf_fused<KT><<<fgrid, UFF_THREADS, 0, st>>>(reinterpret_cast<const KT*>(h->d_ckey), h->d_crec, h->d_fbox, h->d_spts,
                                                                               reinterpret_cast<const KT*>(h->d_hkeys), h->d_hvals, h->d_counts, h->d_parent,
-                                                                              g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, h->uf_row_inner));
+                                                                              g, r2, h->uf_light, h->d_heavy1, h->d_heavy2, h->heavy_cap, h->uf_row_inner, h->uf_tile_batches));
         } else if (h->uf_xmode == 1) {
             int sgrid = (M + UFS_THREADS - 1) / UFS_THREADS;
             if (sgrid > h->num_sms * 8) sgrid = h->num_sms * 8;
@@ -819,7 +822,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         if (const char* e = getenv("MOT_L2_PERSIST")) h->l2_persist_mb = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_L2_WHAT")) h->l2_persist_what = atoi(e);
         if (h->l2_persist_mb > 0) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)h->l2_persist_mb << 20));
+        if (const char* e = getenv("MOT_UF_TILE")) h->uf_tile_batches = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_UF_ROWINNER")) h->uf_row_inner = atoi(e);
+        if (const char* e = getenv("MOT_CLD_THREADS")) { const int v = atoi(e); if (v == 128 || v == 256 || v == 512) h->cld_threads = v; }
         if (const char* e = getenv("MOT_CELL_DENSE")) h->cell_dense = atoi(e);
         if (const char* e = getenv("MOT_UF_AUTO")) h->uf_auto_points = std::max(0, atoi(e));
         if (const char* e = getenv("MOT_UF_LIGHT")) h->uf_light = std::min(4096, std::max(1, atoi(e)));
