@@ -152,6 +152,25 @@ int mot_result_grid(mot_handle* h, int32_t* fine_cells, int32_t* coarse_cells, i
  * cells, [1] coarse cells, [2] clusters, [3] indices, [4] flags, [5] kept points, [9]/[10] fine-cell pairs handed to the
  * cooperative witness search (ring 1 / ring 2), [12] pairs searched serially because that list was full; up to 16 ints. */
 int mot_result_counters(mot_handle* h, int32_t* out, int capacity);
+/* Speculative grid plan (no reference counterpart; PCL builds its KD-tree from scratch every frame, MOT.cpp:472-473).  A
+ * clustering call on an already compacted cloud (mot_cluster*, mot_frame* without removeStatic) first tries the voxel grid of
+ * the handle's previous call, padded to the range of its key bits: no bounding-box pass and no host round trip before the keys.
+ * The key kernel checks every point; a cloud that left the planned grid is clustered again from its own bounding box (a miss
+ * costs one wasted pass, never a wrong result).  enable: 1 / 0 switch it (and drop the current plan), -1 leaves it; hits /
+ * misses (may be NULL) receive the counts since mot_create.  Default on; MOT_PLAN_SPEC=0 in the environment turns it off. */
+int mot_grid_plan(mot_handle* h, int enable, int* hits, int* misses);
+/* Single-launch path for small frames (no reference counterpart; it exists because a frame of the size the reference tracker
+ * sees -- 65,536 points, MOT.cpp:461-491 -- spends its time in launches, not in kernels).  Single-frame calls (mot_cluster,
+ * mot_frame, mot_frame_device, mot_cluster_pointcloud2) with at most max_points input points (default 131072; environment
+ * MOT_SMALL_POINTS) run removeStatic + clustering + tables as ONE kernel on one thread-block cluster and synchronise once.
+ * A frame that kernel cannot take (a crowded cell, > 4096 clusters, very large clusters) is handed back and clustered by the
+ * general path in the same call -- same results either way.  max_points: >= 0 sets the limit (0 = never), < 0 leaves it;
+ * hits / misses (may be NULL): frames served / handed back since mot_create.  Returns the cluster size in CTAs (0 = the device
+ * cannot schedule the cluster: the path is off) or a negative error. */
+int mot_small_frames(mot_handle* h, int max_points, int* hits, int* misses);
+/* Diagnostics: the GPU's %globaltimer (ns) at the end of every phase of the last small-frame launch, [0] = kernel start, [1..13] =
+ * phases A..M as listed in csrc/frame_small.cuh (taken by one thread of the first CTA; 16 values). */
+int mot_small_frame_phases(mot_handle* h, uint64_t* ns, int capacity);
 /* Union-find diagnostics accumulated since the last call (finds, parent hops, unions, ...; cell_uf.cuh ST_*).  Only a
  * library built with -DMOT_UF_STATS counts (returns 1); the product build returns 0 and zeroes. */
 int mot_debug_stats(mot_handle* h, uint64_t* out, int capacity);

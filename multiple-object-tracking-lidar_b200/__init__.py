@@ -101,6 +101,9 @@ SYMBOLS = {
     "mot_result_counts": (C.c_int, [_H, C.POINTER(_SIZE), C.POINTER(C.c_int32), C.POINTER(_SIZE)]),
     "mot_result_grid": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mot_result_counters": (C.c_int, [_H, _i32, C.c_int]),
+    "mot_grid_plan": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mot_small_frames": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mot_small_frame_phases": (C.c_int, [_H, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_int]),
     "mot_debug_stats": (C.c_int, [_H, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_int]),
     "mot_result_device_ptrs": (C.c_int, [_H] + [C.POINTER(C.c_void_p)] * 5),
     "mot_result_fetch": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, _SIZE, C.c_void_p, C.c_void_p, _SIZE]),
@@ -284,6 +287,29 @@ class Tracker:
         out = np.zeros(16, dtype=np.int32)
         self._ck(self.lib.mot_result_counters(self.h, out, 16))
         return out
+
+    def grid_plan(self, enable=None):
+        """Switch the speculative grid plan (None: leave) and return (hits, misses) since the handle was created."""
+        hits, misses = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mot_grid_plan(self.h, -1 if enable is None else int(bool(enable)), C.byref(hits), C.byref(misses)))
+        return hits.value, misses.value
+
+    def small_frames(self, max_points=None):
+        """Limit of the single-launch small-frame path (None: leave); returns (cluster CTAs, hits, misses)."""
+        hits, misses = C.c_int(0), C.c_int(0)
+        rc = self.lib.mot_small_frames(self.h, -1 if max_points is None else int(max_points), C.byref(hits), C.byref(misses))
+        if rc < 0:
+            self._ck(rc)
+        return rc, hits.value, misses.value
+
+    def small_frame_phases(self):
+        """Nanoseconds spent in each phase of the last small-frame launch (dict phase -> ns)."""
+        t = np.zeros(16, dtype=np.uint64)
+        self._ck(self.lib.mot_small_frame_phases(self.h, t, 16))
+        names = ("front: A rs+compact", "front: B hash insert", "front: C scan", "front: D place", "(gap)", "pairs", "tables: F flatten", "tables: G kept list",
+                 "tables: H rank", "tables: I offsets", "tables: J segments", "tables: K order", "(gap)", "farthest pair", "finish")
+        t = t.astype(np.int64)
+        return {f"{i:02d} {n}": int(t[i + 1] - t[i]) for i, n in enumerate(names) if t[i + 1] >= t[i] > 0}
 
     def debug_stats(self):
         """Union-find counters of a -DMOT_UF_STATS build (None for the product build)."""

@@ -403,10 +403,43 @@ __device__ __forceinline__ bool cand_better(const PairCand& a, const PairCand& b
     if (a.i != b.i) return a.i < b.i;
     return a.j < b.j;
 }
-__device__ __forceinline__ float ref_euc_dist(const float4& a, const float4& b) {  // MOT.cpp:1025-1028, fp64 then float
+__device__ __forceinline__ double ref_euc_sq(const float4& a, const float4& b) {  // MOT.cpp:1025-1028: the fp64 sum under the root
     const double dx = __dsub_rn((double)a.x, (double)b.x), dy = __dsub_rn((double)a.y, (double)b.y), dz = __dsub_rn((double)a.z, (double)b.z);
-    const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return __double2float_rn(__dsqrt_rn(s));
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+__device__ __forceinline__ float ref_euc_dist(const float4& a, const float4& b) {  // ... fp64 root, then float
+    return __double2float_rn(__dsqrt_rn(ref_euc_sq(a, b)));
+}
+// One step of the reference's pair scan: the pair (i, j) replaces `best` iff its float distance is strictly larger.  float(sqrt(s))
+// is monotone in s, so a pair whose s does not exceed the largest s seen so far (`seen_s`) cannot win: no root for it.
+__device__ __forceinline__ void pair_scan_step(const float4& pi, const float4& pj, int i, int j, PairCand& best, double& seen_s) {
+    const double s = ref_euc_sq(pi, pj);
+    if (s > seen_s) {
+        seen_s = s;
+        const float d = __double2float_rn(__dsqrt_rn(s));
+        if (d > best.dist) { best.dist = d; best.i = i; best.j = j; }
+    }
+}
+// best candidate of cands[0 .. slabs) (slabs <= 64), computed by the first two warps of the CTA and returned to every thread
+__device__ __forceinline__ PairCand reduce_cands(const PairCand* cands, int slabs, PairCand* s2 /* shared [2] */) {
+    PairCand best;
+    best.dist = -1.0f; best.i = 0x7fffffff; best.j = 0x7fffffff;
+    if (threadIdx.x < 64) {
+        if ((int)threadIdx.x < slabs) best = cands[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            PairCand other;
+            other.dist = __shfl_xor_sync(kFull, best.dist, o);
+            other.i = __shfl_xor_sync(kFull, best.i, o);
+            other.j = __shfl_xor_sync(kFull, best.j, o);
+            if (cand_better(other, best)) best = other;
+        }
+        if (lane_id() == 0) s2[warp_id()] = best;
+    }
+    __syncthreads();
+    best = s2[0];
+    if (cand_better(s2[1], best)) best = s2[1];
+    return best;
 }
 
 constexpr int FP_THREADS = 256;
@@ -426,14 +459,14 @@ __global__ void __launch_bounds__(FP_THREADS) k_farthest_pair(const float4* __re
     }
     PairCand best;
     best.dist = -1.0f; best.i = 0x7fffffff; best.j = 0x7fffffff;
+    double seen_s = -1.0;
     // rows are dealt to (slab, warp) round-robin; the lanes of a warp sweep j
     const int row_stride = slabs * (FP_THREADS / 32);
     for (int i = slab * (FP_THREADS / 32) + warp_id(); i < n - 1; i += row_stride) {
         const float4 pi = staged ? sp[i] : pts[indices[s + i]];
         for (int j = i + 1 + lane_id(); j < n; j += 32) {
             const float4 pj = staged ? sp[j] : pts[indices[s + j]];
-            const float d = ref_euc_dist(pi, pj);
-            if (d > best.dist) { best.dist = d; best.i = i; best.j = j; }  // j ascending within a lane: strict > keeps the first
+            pair_scan_step(pi, pj, i, j, best, seen_s);  // (i, j) ascending within a lane: strict > keeps the first
         }
     }
 #pragma unroll
@@ -453,6 +486,55 @@ __global__ void __launch_bounds__(FP_THREADS) k_farthest_pair(const float4* __re
     }
 }
 
+// The arithmetic of getCentroid's steps 2 and 3, shared by k_circumcentre and the single-launch small-frame path
+// (frame_small.cuh) so that both produce the same bits.
+struct CcLine {
+    double Pi[3], Pj[3];   // the farthest pair as the reference leaves it after the pair loop (zero if the cluster has < 2 points)
+    double V0, V1, V2, denom;
+};
+__device__ __forceinline__ void cc_line_from_pair(const float4& a, const float4& b, bool have_pair, CcLine& L) {
+    for (int d = 0; d < 3; ++d) { L.Pi[d] = 0.0; L.Pj[d] = 0.0; }
+    L.V0 = 0.0; L.V1 = 0.0; L.V2 = 0.0;
+    if (have_pair) {
+        L.Pi[0] = a.x; L.Pi[1] = a.y; L.Pi[2] = a.z;
+        L.Pj[0] = b.x; L.Pj[1] = b.y; L.Pj[2] = b.z;
+        L.V0 = __ddiv_rn(__dsub_rn(L.Pj[1], L.Pi[1]), __dsub_rn(L.Pj[0], L.Pi[0]));  // MOT.cpp:753
+        L.V1 = -1.0;
+        L.V2 = __dadd_rn(__dmul_rn(L.V0, -L.Pi[0]), L.Pi[1]);                         // MOT.cpp:755
+    }
+    L.denom = __dsqrt_rn(__dadd_rn(__dmul_rn(L.V0, L.V0), __dmul_rn(L.V1, L.V1)));
+}
+// float distance of p from the XY line; `skip` = p equals Pi or Pj (the reference skips those without raising the bar)
+__device__ __forceinline__ float cc_line_dist(const CcLine& L, const float4& p, bool& skip) {
+    const double px = p.x, py = p.y, pz = p.z;
+    const double num = fabs(__dadd_rn(__dadd_rn(__dmul_rn(L.V0, px), __dmul_rn(L.V1, py)), L.V2));
+    const bool eqi = px == L.Pi[0] && py == L.Pi[1] && pz == L.Pi[2];
+    const bool eqj = px == L.Pj[0] && py == L.Pj[1] && pz == L.Pj[2];
+    skip = eqi || eqj;
+    return __double2float_rn(__ddiv_rn(num, L.denom));
+}
+// step 3, MOT.cpp:787-809: float A..G from double expressions, float final arithmetic, no FMA
+__device__ __forceinline__ float4 cc_finish(const CcLine& L, const double Pk[3], float intensity) {
+    const double* Pi = L.Pi;
+    const double* Pj = L.Pj;
+    const float A = __double2float_rn(__dsub_rn(Pj[0], Pi[0]));
+    const float B = __double2float_rn(__dsub_rn(Pj[1], Pi[1]));
+    const float C = __double2float_rn(__dsub_rn(Pk[0], Pi[0]));
+    const float D = __double2float_rn(__dsub_rn(Pk[1], Pi[1]));
+    const float E = __double2float_rn(__dadd_rn(__dmul_rn((double)A, __dadd_rn(Pi[0], Pj[0])), __dmul_rn((double)B, __dadd_rn(Pi[1], Pj[1]))));
+    const float F = __double2float_rn(__dadd_rn(__dmul_rn((double)C, __dadd_rn(Pi[0], Pk[0])), __dmul_rn((double)D, __dadd_rn(Pi[1], Pk[1]))));
+    const float G = __double2float_rn(__dmul_rn(2.0, __dsub_rn(__dmul_rn((double)A, __dsub_rn(Pk[1], Pj[1])), __dmul_rn((double)B, __dsub_rn(Pk[0], Pj[0])))));
+    float4 o;
+    if (G == 0.0f) { o.x = __double2float_rn(Pi[0]); o.y = __double2float_rn(Pi[1]); }
+    else {
+        o.x = __fdiv_rn(__fsub_rn(__fmul_rn(D, E), __fmul_rn(B, F)), G);
+        o.y = __fdiv_rn(__fsub_rn(__fmul_rn(A, F), __fmul_rn(C, E)), G);
+    }
+    o.z = 0.0f;
+    o.w = intensity;
+    return o;
+}
+
 constexpr int CC_THREADS = 128;
 __global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __restrict__ pts, const int* __restrict__ cl_offsets,
                                                               const uint32_t* __restrict__ indices, int K, int slabs,
@@ -461,37 +543,24 @@ __global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __res
                                                               const int* __restrict__ frame_cl_offsets = nullptr, int n_frames = 1) {
     __shared__ float sdist[CC_THREADS / 32];
     __shared__ int sk[CC_THREADS / 32];
+    __shared__ PairCand s2[2];
     for (int c = blockIdx.x; c < K; c += gridDim.x) {
         const int s = cl_offsets[c], n = cl_offsets[c + 1] - s;
-        PairCand best;
-        best.dist = -1.0f; best.i = 0x7fffffff; best.j = 0x7fffffff;
-        for (int t = 0; t < slabs; ++t) {
-            const PairCand o = cands[(size_t)c * slabs + t];
-            if (cand_better(o, best)) best = o;
-        }
-        // Pi, Pj, Vij as the reference leaves them after the pair loop (zero if the cluster has < 2 points)
-        double Pi[3] = {0, 0, 0}, Pj[3] = {0, 0, 0}, V0 = 0, V1 = 0, V2 = 0;
-        if (best.dist >= 0.0f) {
-            const float4 a = pts[indices[s + best.i]], b = pts[indices[s + best.j]];
-            Pi[0] = a.x; Pi[1] = a.y; Pi[2] = a.z;
-            Pj[0] = b.x; Pj[1] = b.y; Pj[2] = b.z;
-            V0 = __ddiv_rn(__dsub_rn(Pj[1], Pi[1]), __dsub_rn(Pj[0], Pi[0]));  // MOT.cpp:753
-            V1 = -1.0;
-            V2 = __dadd_rn(__dmul_rn(V0, -Pi[0]), Pi[1]);                      // MOT.cpp:755
+        const PairCand best = reduce_cands(cands + (size_t)c * slabs, slabs, s2);
+        CcLine L;
+        {
+            const bool have = best.dist >= 0.0f;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            cc_line_from_pair(have ? pts[indices[s + best.i]] : z, have ? pts[indices[s + best.j]] : z, have, L);
         }
         // step 2: first k with strictly largest float line distance, skipping points equal to Pi / Pj.
         // (the reference only updates dist_max when the point is accepted, so skipped points do not raise the bar)
-        const double denom = __dsqrt_rn(__dadd_rn(__dmul_rn(V0, V0), __dmul_rn(V1, V1)));
         float bd = -1.0f;
         int bk = 0x7fffffff;
         for (int k = threadIdx.x; k < n; k += CC_THREADS) {
-            const float4 p = pts[indices[s + k]];
-            const double px = p.x, py = p.y, pz = p.z;
-            const double num = fabs(__dadd_rn(__dadd_rn(__dmul_rn(V0, px), __dmul_rn(V1, py)), V2));
-            const float d = __double2float_rn(__ddiv_rn(num, denom));
-            const bool eqi = px == Pi[0] && py == Pi[1] && pz == Pi[2];
-            const bool eqj = px == Pj[0] && py == Pj[1] && pz == Pj[2];
-            if (d > bd && !eqi && !eqj) { bd = d; bk = k; }  // NaN distances never satisfy >, as in the reference
+            bool skip;
+            const float d = cc_line_dist(L, pts[indices[s + k]], skip);
+            if (d > bd && !skip) { bd = d; bk = k; }  // NaN distances never satisfy >, as in the reference
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -510,22 +579,7 @@ __global__ void __launch_bounds__(CC_THREADS) k_circumcentre(const float4* __res
                 const float4 p = pts[indices[s + bk]];
                 Pk[0] = p.x; Pk[1] = p.y; Pk[2] = p.z;
             }
-            // step 3, MOT.cpp:787-809: float A..G from double expressions, float final arithmetic, no FMA
-            const float A = __double2float_rn(__dsub_rn(Pj[0], Pi[0]));
-            const float B = __double2float_rn(__dsub_rn(Pj[1], Pi[1]));
-            const float C = __double2float_rn(__dsub_rn(Pk[0], Pi[0]));
-            const float D = __double2float_rn(__dsub_rn(Pk[1], Pi[1]));
-            const float E = __double2float_rn(__dadd_rn(__dmul_rn((double)A, __dadd_rn(Pi[0], Pj[0])), __dmul_rn((double)B, __dadd_rn(Pi[1], Pj[1]))));
-            const float F = __double2float_rn(__dadd_rn(__dmul_rn((double)C, __dadd_rn(Pi[0], Pk[0])), __dmul_rn((double)D, __dadd_rn(Pi[1], Pk[1]))));
-            const float G = __double2float_rn(__dmul_rn(2.0, __dsub_rn(__dmul_rn((double)A, __dsub_rn(Pk[1], Pj[1])), __dmul_rn((double)B, __dsub_rn(Pk[0], Pj[0])))));
-            float4 o;
-            if (G == 0.0f) { o.x = __double2float_rn(Pi[0]); o.y = __double2float_rn(Pi[1]); }
-            else {
-                o.x = __fdiv_rn(__fsub_rn(__fmul_rn(D, E), __fmul_rn(B, F)), G);
-                o.y = __fdiv_rn(__fsub_rn(__fmul_rn(A, F), __fmul_rn(C, E)), G);
-            }
-            o.z = 0.0f;
-            o.w = intensity;
+            float4 o = cc_finish(L, Pk, intensity);
             if (frame_stamps) {  // batch: the stamp of the frame that owns cluster c (largest f with frame_cl_offsets[f] <= c)
                 int lo = 0, hi = n_frames - 1;
                 while (lo < hi) {

@@ -76,18 +76,29 @@ __device__ __forceinline__ int frame_of(const int* __restrict__ frame_offsets, i
 }
 
 // K1: voxel key per point (fp64 cell coordinates: an fp32 product could misplace a point by a cell).
-template <typename KT>
-__global__ void __launch_bounds__(256) k_cell_keys(const float4* __restrict__ pts, int m, GridCodec g,
-                                                    const int* __restrict__ frame_offsets, KT* __restrict__ keys) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const float4 p = ld_stream(pts + i);
-    int ix = __double2int_rd(__dmul_rn(__dsub_rn((double)p.x, g.minx), g.inv_e));
-    int iy = __double2int_rd(__dmul_rn(__dsub_rn((double)p.y, g.miny), g.inv_e));
-    int iz = __double2int_rd(__dmul_rn(__dsub_rn((double)p.z, g.minz), g.inv_e));
+// A point outside the grid (flag 32) or with a non-finite coordinate (flag 64) is reported: with a grid planned from this
+// call's own bounding box neither can happen; with the handle's SPECULATIVE plan (the grid of its previous call, no bounding
+// box pass and no host round trip before the keys) the first one tells the host to plan again and rerun.
+__device__ __forceinline__ void cell_coords_checked(const GridCodec& g, const float4& p, int& ix, int& iy, int& iz, int* __restrict__ flags) {
+    ix = __double2int_rd(__dmul_rn(__dsub_rn((double)p.x, g.minx), g.inv_e));
+    iy = __double2int_rd(__dmul_rn(__dsub_rn((double)p.y, g.miny), g.inv_e));
+    iz = __double2int_rd(__dmul_rn(__dsub_rn((double)p.z, g.minz), g.inv_e));
+    const bool finite = (fabsf(p.x) < INFINITY) && (fabsf(p.y) < INFINITY) && (fabsf(p.z) < INFINITY);
+    if (!finite) atomicOr(flags, 64);
+    else if (ix < 0 || iy < 0 || iz < 0 || ix >= g.nfx || iy >= g.nfy || iz >= g.nfz) atomicOr(flags, 32);
     ix = min(max(ix, 0), g.nfx - 1);
     iy = min(max(iy, 0), g.nfy - 1);
     iz = min(max(iz, 0), g.nfz - 1);
+}
+
+template <typename KT>
+__global__ void __launch_bounds__(256) k_cell_keys(const float4* __restrict__ pts, int m, GridCodec g,
+                                                    const int* __restrict__ frame_offsets, KT* __restrict__ keys, int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float4 p = ld_stream(pts + i);
+    int ix, iy, iz;
+    cell_coords_checked(g, p, ix, iy, iz, flags);
     const int frame = g.n_frames > 1 ? frame_of(frame_offsets, g.n_frames, i) : 0;
     keys[i] = key_compose<KT>(g, frame, ix, iy, iz);
 }

@@ -35,6 +35,7 @@
 #include "cell_uf.cuh"
 #include "cluster_table.cuh"
 #include "common.cuh"
+#include "frame_small.cuh"
 #include "grid_uf.cuh"
 #include "ihgp.cuh"
 #include "radix_sort.cuh"
@@ -52,7 +53,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_FS_FRONT, KID_FS_EDGES, KID_FS_COMPRESS, KID_FS_LINK, KID_FS_TABLES, KID_FS_FARTHEST, KID_FS_FINISH, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -60,7 +61,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build", "k_fs_front", "k_fs_edges", "k_fs_compress", "k_fs_link", "k_fs_tables", "k_fs_farthest", "k_fs_finish"};
 
 struct mot_handle {
     int device = 0;
@@ -108,6 +109,26 @@ struct mot_handle {
     int* d_frame_offsets_in = nullptr;  // ... of the input cloud, before removeStatic
     unsigned* d_c1p_status = nullptr;  // one-pass compaction: tile status words + ticket
     size_t c1p_tiles = 0;
+    // speculative grid plan: the grid of the previous call on this handle, padded to the power-of-two range of its key bits
+    bool plan_valid = false;
+    GridCodec plan_g{};
+    int plan_bits = 0;
+    float plan_tol = 0.0f;
+    int plan_spec = 1;        // MOT_PLAN_SPEC=0: always take the bounding box first (one more kernel and one more host round trip per call)
+    int plan_hits = 0, plan_misses = 0;
+    // single-launch path for small frames (frame_small.cuh)
+    int fs_cluster = 0;            // CTAs of the cluster (16 or 8; 0 = not available)
+    int fs_max_points = 131072;    // MOT_SMALL_POINTS: frames of at most this many input points try it (0 = never)
+    int fs_cell_cap = 64;          // MOT_SMALL_CELLCAP: a fine cell with more points hands the frame to the general path
+    int* d_fs_state = nullptr;
+    FsArgs* d_fs_args = nullptr;   // the kernels read their arguments from device memory, so that one instantiated graph serves every call
+    FsArgs* h_fs_args = nullptr;   // pinned staging of the arguments (source of the graph's copy node)
+    cudaGraphExec_t fs_graph = nullptr;
+    int fs_use_graph = 1;          // MOT_SMALL_GRAPH=0: five plain launches instead of one graph launch
+    int fs_skip = 0;               // calls left that go straight to the general path after a fallback
+    int fs_hits = 0, fs_misses = 0;
+    bool tim_stages = true;        // false: the last call recorded only its first and last event (small-frame path)
+    unsigned long long* d_fs_phase_ns = nullptr;
     int keys_hist_fused = 0;  // MOT_KEYS_HIST=1: k_cell_keys_hist instead of k_cell_keys + the first k_rs_hist (measured neutral: 107 + 2x35 vs 81 + 3x32 us)
     int csr_compact = 1;      // drop the points of filtered-out components before the CSR sort when they are >= 40 % (c2: 77 %, 367 -> 259 us); MOT_CSR_COMPACT=0: always sort all
     int rs_mode = 1;  // 1: single-pass compaction (decoupled look-back); 0: count + compact (MOT_RS_MODE)
@@ -307,6 +328,14 @@ int reset_bbox(mot_handle* h) {
     return MOT_OK;
 }
 
+// Start of a single-frame call: nothing is enqueued yet -- the small-frame graph clears its own counters, and frame_core
+// calls reset_frame_state when the frame takes the general path.
+void begin_frame(mot_handle* h) {
+    h->prof.launches = 0;
+    h->have_result = false;
+    h->tim_stages = true;
+}
+
 int reset_frame_state(mot_handle* h) {
     static const int bbox_init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0, 0};
     CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), h->stream));
@@ -328,10 +357,10 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
     if (h->keys_hist_fused && h->rws.mode == 0) {
         const RsPlan pl = rs_plan(M, total_bits, h->rws);
         LAUNCH(KID_KEYS, k_cell_keys_hist<KT><<<pl.ck.grid, RS_THREADS, ((size_t)1 << pl.bits0) * sizeof(unsigned), st>>>(cloud, M, pl.ck.chunk, g, h->d_frame_offsets,
-                                                                                                                       keys[0], pl.bits0, h->rws.hist));
+                                                                                                                       keys[0], pl.bits0, h->rws.hist, h->d_counts + CNT_FLAGS));
         h->rws.first_hist_done = true;
     } else {
-        LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0]));
+        LAUNCH(KID_KEYS, k_cell_keys<KT><<<(M + 255) / 256, 256, 0, st>>>(cloud, M, g, h->d_frame_offsets, keys[0], h->d_counts + CNT_FLAGS));
     }
     const int sb = radix_sort_pairs<KT>(st, keys, h->d_vals, M, total_bits, true, h->rws, h->prof, KID_SORT_HIST);
     h->rws.first_hist_done = false;
@@ -493,19 +522,27 @@ int cluster_sorted_part(mot_handle* h, const float4* cloud, int M, const GridCod
 
 int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, bool with_centroids, double stamp) {
     cudaStream_t st = h->stream;
-    if (m_known >= 0) {
+    // Speculation: a sensor's extent hardly changes from call to call, so the grid of the previous call (padded, see below) is
+    // tried first -- no bounding-box kernel, no host round trip before the keys.  k_cell_keys verifies every point (flag 32).
+    const bool spec = h->plan_spec && h->plan_valid && m_known > 0 && h->plan_g.n_frames == n_frames && h->plan_tol == h->tol;
+    GridCodec g{};
+    int total_bits = 0;
+    int M = m_known;
+    if (!spec) {
         if (m_known > 0) {
             int grid = (m_known + 255) / 256;
             if (grid > h->num_sms * 8) grid = h->num_sms * 8;
             LAUNCH(KID_BBOX, k_bbox<<<grid, 256, 0, st>>>(cloud, m_known, h->d_bbox));
         }
+        CK(cudaEventRecord(h->ev[1], st));
+        // ---- S1 ----
+        CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(mot_sync(h));
+        M = m_known >= 0 ? m_known : h->h_pinned[8 + CNT_M];
+    } else {
+        CK(cudaEventRecord(h->ev[1], st));
     }
-    CK(cudaEventRecord(h->ev[1], st));
-    // ---- S1 ----
-    CK(cudaMemcpyAsync(h->h_pinned, h->d_bbox, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(mot_sync(h));
-    const int M = m_known >= 0 ? m_known : h->h_pinned[8 + CNT_M];
     h->res_cloud = cloud;
     h->res_M = M;
     h->res_K = 0;
@@ -513,7 +550,7 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_frames = n_frames;
     h->res_centroids = false;
     h->res_fine = h->res_coarse = h->res_key_bits = 0;
-    if (h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
+    if (!spec && h->h_pinned[6] != 0) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
     if (M == 0) {
         for (int i = 1; i < 6; ++i) CK(cudaEventRecord(h->ev[i], st));
         CK(cudaMemsetAsync(h->d_cl_offsets, 0, sizeof(int), st));
@@ -521,29 +558,62 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
         h->have_result = true;
         return MOT_OK;
     }
-    float mn[3], mx[3];
-    for (int d = 0; d < 3; ++d) {
-        mn[d] = ordered_to_float_bits(h->h_pinned[d]);
-        mx[d] = ordered_to_float_bits(h->h_pinned[3 + d]);
-    }
-    GridCodec g{};
-    const double hcell = (double)h->tol * (1.0 + 1.0 / 1024.0);  // coarse edge: tol * (1 + 2^-10)
-    const double e = hcell * 0.5;                               // fine (clique) edge
-    g.inv_e = 1.0 / e;
-    g.minx = mn[0]; g.miny = mn[1]; g.minz = mn[2];
-    long long nf[3];
-    for (int d = 0; d < 3; ++d) {
-        const double span = ((double)mx[d] - (double)mn[d]) * g.inv_e;
-        if (!(span < 1.0e9)) return fail(h, MOT_ERR_INVALID, "cloud extent / cluster_tolerance too large for the voxel grid");
-        nf[d] = (long long)std::floor(span) + 1;
-    }
-    g.nfx = (int)nf[0]; g.nfy = (int)nf[1]; g.nfz = (int)nf[2];
-    g.ncx = (g.nfx + 1) / 2; g.ncy = (g.nfy + 1) / 2; g.ncz = (g.nfz + 1) / 2;
-    g.bx = ceil_log2(g.ncx); g.by = ceil_log2(g.ncy); g.bz = ceil_log2(g.ncz);
-    g.n_frames = n_frames;
     const int frame_bits = n_frames > 1 ? ceil_log2(n_frames) : 0;
-    const int total_bits = 3 + g.bx + g.by + g.bz + frame_bits;
-    if (total_bits > 63) return fail(h, MOT_ERR_INVALID, "voxel key does not fit in 64 bits");
+    if (spec) {
+        g = h->plan_g;
+        total_bits = h->plan_bits;
+    } else {
+        float mn[3], mx[3];
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = ordered_to_float_bits(h->h_pinned[d]);
+            mx[d] = ordered_to_float_bits(h->h_pinned[3 + d]);
+        }
+        const double hcell = (double)h->tol * (1.0 + 1.0 / 1024.0);  // coarse edge: tol * (1 + 2^-10)
+        const double e = hcell * 0.5;                               // fine (clique) edge
+        g.inv_e = 1.0 / e;
+        g.minx = mn[0]; g.miny = mn[1]; g.minz = mn[2];
+        long long nf[3];
+        for (int d = 0; d < 3; ++d) {
+            const double span = ((double)mx[d] - (double)mn[d]) * g.inv_e;
+            if (!(span < 1.0e9)) return fail(h, MOT_ERR_INVALID, "cloud extent / cluster_tolerance too large for the voxel grid");
+            nf[d] = (long long)std::floor(span) + 1;
+        }
+        g.nfx = (int)nf[0]; g.nfy = (int)nf[1]; g.nfz = (int)nf[2];
+        g.ncx = (g.nfx + 1) / 2; g.ncy = (g.nfy + 1) / 2; g.ncz = (g.nfz + 1) / 2;
+        g.bx = ceil_log2(g.ncx); g.by = ceil_log2(g.ncy); g.bz = ceil_log2(g.ncz);
+        g.n_frames = n_frames;
+        total_bits = 3 + g.bx + g.by + g.bz + frame_bits;
+        if (total_bits > 63) return fail(h, MOT_ERR_INVALID, "voxel key does not fit in 64 bits");
+        // The plan for the next call: the same key layout, every axis widened to the full range of its bits (and by the bits
+        // that are free up to the next radix pass), the origin moved so that the slack lies on both sides of this call's box.
+        {
+            GridCodec pg = g;
+            int bits[3] = {g.bx, g.by, g.bz};
+            const int passes = (total_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+            int spare = std::min(passes * RS_MAX_BITS, total_bits <= 32 ? 32 : 63) - total_bits;
+            const int nc00[3] = {g.ncx, g.ncy, g.ncz};
+            for (int d = 0; d < 3 && spare > 0; ++d)  // an axis that fills its bits exactly has no slack: it gets a free bit
+                if ((1 << bits[d]) == nc00[d]) {
+                    ++bits[d];
+                    --spare;
+                }
+            const int nc0[3] = {g.ncx, g.ncy, g.ncz};
+            double pmin[3] = {g.minx, g.miny, g.minz};
+            int ncp[3];
+            for (int d = 0; d < 3; ++d) {
+                ncp[d] = 1 << bits[d];
+                pmin[d] -= (double)((ncp[d] - nc0[d]) / 2) * hcell;
+            }
+            pg.minx = pmin[0]; pg.miny = pmin[1]; pg.minz = pmin[2];
+            pg.bx = bits[0]; pg.by = bits[1]; pg.bz = bits[2];
+            pg.ncx = ncp[0]; pg.ncy = ncp[1]; pg.ncz = ncp[2];
+            pg.nfx = 2 * ncp[0]; pg.nfy = 2 * ncp[1]; pg.nfz = 2 * ncp[2];
+            h->plan_g = pg;
+            h->plan_bits = 3 + bits[0] + bits[1] + bits[2] + frame_bits;
+            h->plan_tol = h->tol;
+            h->plan_valid = h->plan_bits <= 63;
+        }
+    }
     int rc = total_bits <= 32 ? cluster_sorted_part<uint32_t>(h, cloud, M, g, total_bits, n_frames)
                               : cluster_sorted_part<uint64_t>(h, cloud, M, g, total_bits, n_frames);
     if (rc != MOT_OK) return rc;
@@ -571,6 +641,19 @@ int cluster_core(mot_handle* h, const float4* cloud, int m_known, int n_frames, 
     h->res_K = K;
     h->res_total = total;
     std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
+    if (h->h_pinned[8 + CNT_FLAGS] & 64) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
+    if (h->h_pinned[8 + CNT_FLAGS] & 32) {
+        if (!spec) return fail(h, MOT_ERR_CUDA, "internal: a point fell outside the grid planned from its own bounding box");
+        // the cloud outgrew the speculative grid: plan from this call's bounding box and run again (the work so far is void)
+        h->plan_valid = false;
+        ++h->plan_misses;
+        const int launches_so_far = h->prof.launches;
+        int rc2 = reset_frame_state(h);
+        if (rc2 != MOT_OK) return rc2;
+        h->prof.launches = launches_so_far;
+        return cluster_core(h, cloud, m_known, n_frames, with_centroids, stamp);
+    }
+    if (spec) ++h->plan_hits;
     if (h->h_pinned[8 + CNT_FLAGS] & 1) return fail(h, MOT_ERR_CAPACITY, "dense-task list overflow (internal capacity)");
     if (h->h_pinned[8 + CNT_FLAGS] & 16) return fail(h, MOT_ERR_CUDA, "internal self check failed (MOT_CHECKS build): an index left its bounds in cell_uf.cuh");
     if (h->h_pinned[8 + CNT_FLAGS] & 8) return fail(h, MOT_ERR_CUDA, "TMA staging of a cell tile timed out (mbarrier never completed)");
@@ -676,6 +759,14 @@ void fold_profile(mot_handle* h) {
 int finish_timings(mot_handle* h) {
     CK(mot_sync(h));
     float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
+    if (!h->tim_stages) {  // small-frame path: one graph, only the total is measured
+        cudaEventElapsedTime(&t05, h->ev[0], h->ev[5]);
+        cudaGetLastError();
+        h->tim = mot_timings{};
+        h->tim.total_ms = t05;
+        fold_profile(h);
+        return MOT_OK;
+    }
     cudaEventElapsedTime(&t01, h->ev[0], h->ev[1]);
     cudaEventElapsedTime(&t12, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&t23, h->ev[2], h->ev[3]);
@@ -728,6 +819,171 @@ int check_frame_args(mot_handle* h, const void* pts, size_t n) {
     if (n > h->max_points) return fail(h, MOT_ERR_CAPACITY, "frame larger than the handle's max_points");
     if (n > 0x7ffffff0ull) return fail(h, MOT_ERR_CAPACITY, "frame too large");
     return MOT_OK;
+}
+
+// Small frames (frame_small.cuh): removeStatic + clustering + tables as five kernels launched back to back -- as ONE
+// instantiated CUDA graph -- with a single host round trip at the end; every size in between (M, cells, K) stays on the device.
+// The kernels of the small-frame path on `st`: counters cleared, arguments copied from their pinned staging, five kernels, counters
+// copied back.  Called directly (profiling / MOT_SMALL_GRAPH=0) or under stream capture (once per handle).
+int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
+    const int wide_grid = h->num_sms * 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->fs_cluster);
+    cfg.blockDim = dim3(FS_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->fs_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const FsArgs* ap = h->d_fs_args;
+    CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), st));
+    CK(cudaMemcpyAsync(h->d_fs_args, h->h_fs_args, sizeof(FsArgs), cudaMemcpyHostToDevice, st));
+    if (with_prof) {
+        LAUNCH(KID_FS_FRONT, CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap)));
+        LAUNCH(KID_FS_EDGES, k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap));
+        LAUNCH(KID_FS_COMPRESS, k_fs_compress<<<h->num_sms, FS_PAIR_THREADS, 0, st>>>(ap));
+        LAUNCH(KID_FS_LINK, k_fs_link<<<wide_grid / 2, FS_PAIR_THREADS, 0, st>>>(ap));
+        LAUNCH(KID_FS_TABLES, CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap)));
+        LAUNCH(KID_FS_FARTHEST, k_fs_farthest<<<wide_grid, FS_FP_THREADS, 0, st>>>(ap));
+        LAUNCH(KID_FS_FINISH, k_fs_finish<<<h->num_sms * 2, FS_FIN_THREADS, 0, st>>>(ap));
+    } else {
+        CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap));
+        k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap);
+        k_fs_compress<<<h->num_sms, FS_PAIR_THREADS, 0, st>>>(ap);
+        k_fs_link<<<wide_grid / 2, FS_PAIR_THREADS, 0, st>>>(ap);
+        CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap));
+        k_fs_farthest<<<wide_grid, FS_FP_THREADS, 0, st>>>(ap);
+        k_fs_finish<<<h->num_sms * 2, FS_FIN_THREADS, 0, st>>>(ap);
+    }
+    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return MOT_OK;
+}
+
+int fs_build_graph(mot_handle* h) {
+    cudaStream_t st = h->stream;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = fs_enqueue(h, st, false);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != MOT_OK || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        h->fs_use_graph = 0;  // plain launches from now on
+        return rc != MOT_OK ? rc : MOT_OK;
+    }
+    const cudaError_t e2 = cudaGraphInstantiate(&h->fs_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e2 != cudaSuccess) {
+        cudaGetLastError();
+        h->fs_graph = nullptr;
+        h->fs_use_graph = 0;
+    }
+    return MOT_OK;
+}
+
+// Returns MOT_OK (result ready), 1 (not taken), 2 (launched but handed back: the caller restarts the frame on the general
+// path), < 0 on errors.
+int frame_small(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_dst, bool with_centroids, double stamp) {
+    if (h->fs_cluster == 0 || h->fs_max_points == 0 || n <= 0 || n > h->fs_max_points) return 1;
+    if ((long long)n > (long long)h->fs_cluster * FS_THREADS * FS_MAX_ITEMS) return 1;
+    if (h->fs_skip > 0) { --h->fs_skip; return 1; }
+    const int wide_grid = h->num_sms * 8;
+    int rc = ensure_tables(h, (size_t)std::min(n, FS_MAX_K), (size_t)FS_MAX_K + (size_t)wide_grid);
+    if (rc != MOT_OK) return rc;
+    cudaStream_t st = h->stream;
+    FsArgs a{};
+    a.src = src; a.n = n; a.do_rs = do_rs ? 1 : 0; a.mp = h->mp; a.bits = h->d_bits; a.kept = rs_dst;
+    a.inv_e = 2.0 / ((double)h->tol * (1.0 + 1.0 / 1024.0));
+    a.r2 = (float)((double)h->tol * (double)h->tol);
+    a.min_size = h->min_size; a.max_size = h->max_size;
+    a.with_centroids = with_centroids ? 1 : 0;
+    a.stamp = (float)stamp;
+    a.cell_cap = h->fs_cell_cap;
+    a.fp_ctas = wide_grid;
+    a.order_limit = with_centroids ? (1ull << 22) : (1ull << 25);
+    a.log_t = std::max(4, ceil_log2(2 * (long long)n));
+    a.T = 1 << a.log_t;  // <= hash_capacity (2^ceil_log2(2 max_points))
+    a.hkeys = reinterpret_cast<unsigned long long*>(h->d_hkeys);
+    a.hstart = h->d_hvals;
+    a.pslot = reinterpret_cast<int*>(h->d_keys[0]);
+    a.prank = reinterpret_cast<int*>(h->d_keys[1]);
+    a.spts = h->d_spts;
+    a.scell = reinterpret_cast<int*>(h->d_croots[1]);
+    a.celllist = reinterpret_cast<int*>(h->d_crec);
+    a.edges = reinterpret_cast<int2*>(h->d_nbr);
+    a.edge_cap = (int)std::min<size_t>(h->max_points * 8, 0x7fffffff);
+    a.fbox = h->d_fbox;
+    a.state = h->d_fs_state;
+    a.parent = h->d_parent; a.root = h->d_root; a.csize = h->d_csize; a.cmin = h->d_cmin; a.crank = h->d_crank;
+    a.ksize = reinterpret_cast<int*>(h->d_croots[0]);
+    a.kmin = reinterpret_cast<int*>(h->d_ckeys[0]);
+    a.kroot = reinterpret_cast<int*>(h->d_ckeys[1]);
+    a.ssize = h->d_fc_start;
+    a.cursor = h->d_cc_first;
+    a.idx_tmp = h->d_vals[1];
+    a.cands = h->d_cands;
+    a.labels = h->d_labels; a.cl_offsets = h->d_cl_offsets; a.indices = h->d_vals[0];
+    a.stats = h->d_stats; a.centroids = h->d_centroids; a.counts = h->d_counts;
+    a.phase_ns = h->d_fs_phase_ns;
+    *h->h_fs_args = a;  // the previous call on this handle has been synchronised: the staging is free
+    if (h->fs_use_graph && !h->prof.on) {
+        if (!h->fs_graph) {
+            rc = fs_build_graph(h);
+            if (rc != MOT_OK) return rc;
+        }
+    }
+    if (h->fs_use_graph && !h->prof.on && h->fs_graph) {
+        CK(cudaGraphLaunch(h->fs_graph, st));
+        h->prof.launches += 7;
+    } else {
+        rc = fs_enqueue(h, st, true);
+        if (rc != MOT_OK) return rc;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(h->ev[5], st));
+    h->tim_stages = false;
+    CK(mot_sync(h));
+    const int flags = h->h_pinned[8 + CNT_FLAGS];
+    if (flags & FS_FLAG_NONFINITE) return fail(h, MOT_ERR_NONFINITE, "cloud contains NaN/Inf coordinates");
+    if (flags != 0) {  // FS_FLAG_FALLBACK: a crowded cell / too many clusters / coordinates beyond the hash key
+        ++h->fs_misses;
+        h->fs_skip = 15;
+        return 2;
+    }
+    ++h->fs_hits;
+    h->res_cloud = do_rs ? rs_dst : src;
+    h->res_M = h->h_pinned[8 + CNT_M];
+    h->res_K = h->h_pinned[8 + CNT_K];
+    h->res_total = h->h_pinned[8 + CNT_TOTAL];
+    h->res_frames = 1;
+    h->res_centroids = with_centroids;
+    h->res_idx_buf = 0;
+    h->res_fine = h->h_pinned[8 + CNT_COARSE];
+    h->res_coarse = 0;
+    h->res_key_bits = 0;
+    std::memcpy(h->res_counters, h->h_pinned + 8, sizeof(h->res_counters));
+    h->have_result = true;
+    return MOT_OK;
+}
+
+// One frame: removeStatic (optional, src -> rs_dst) + clustering.  Small frames first try the single-launch path.
+int frame_core(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_dst, bool with_centroids, double stamp) {
+    int rc = frame_small(h, src, n, do_rs, rs_dst, with_centroids, stamp);
+    if (rc <= 0) return rc;
+    {   // the general path starts from cleared counters (also after a small-frame launch that was handed back)
+        const int launches = h->prof.launches;
+        rc = reset_frame_state(h);
+        if (rc != MOT_OK) return rc;
+        h->prof.launches = launches;
+        h->tim_stages = true;
+    }
+    if (do_rs && n > 0) {
+        rc = enqueue_remove_static(h, src, n, rs_dst);
+        if (rc != MOT_OK) return rc;
+        return cluster_core(h, rs_dst, -1, 1, with_centroids, stamp);
+    }
+    return cluster_core(h, do_rs ? rs_dst : src, n, 1, with_centroids, stamp);
 }
 
 // compute centroids for an existing result that was produced without them
@@ -873,6 +1129,38 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         h->rws.err_flag = h->d_counts + CNT_FLAGS;
         if (const char* e = getenv("MOT_SORT_MODE")) h->rws.mode = atoi(e);
         if (const char* e = getenv("MOT_SORT_BIGTILE")) h->rws.big_tile_from = atoi(e);
+        if (const char* e = getenv("MOT_PLAN_SPEC")) h->plan_spec = atoi(e);
+        if (const char* e = getenv("MOT_SMALL_POINTS")) h->fs_max_points = std::max(0, atoi(e));
+        if (const char* e = getenv("MOT_SMALL_CELLCAP")) h->fs_cell_cap = std::max(1, atoi(e));
+        CK(dalloc(&h->d_fs_state, (size_t)FS_ST_N));
+        CK(dalloc(&h->d_fs_args, (size_t)1));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_fs_args), sizeof(FsArgs), cudaHostAllocDefault));
+        if (const char* e = getenv("MOT_SMALL_GRAPH")) h->fs_use_graph = atoi(e);
+        CK(dalloc(&h->d_fs_phase_ns, (size_t)FS_PHASES));
+        CK(cudaMemset(h->d_fs_phase_ns, 0, FS_PHASES * sizeof(unsigned long long)));
+        {   // the small-frame kernel runs as one cluster: 16 CTAs where the device schedules them (non-portable size), else 8
+            int want = 16;
+            if (const char* e = getenv("MOT_SMALL_CLUSTER")) want = atoi(e);
+            cudaFuncSetAttribute(k_fs_front, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(k_fs_tables, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            for (int c = want; c >= 1 && h->fs_cluster == 0; c >>= 1) {
+                if (c > 16) continue;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(c);
+                cfg.blockDim = dim3(FS_THREADS);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                int n_clusters = 0;
+                int n2 = 0;
+                if (cudaOccupancyMaxActiveClusters(&n_clusters, k_fs_front, &cfg) == cudaSuccess && n_clusters >= 1 &&
+                    cudaOccupancyMaxActiveClusters(&n2, k_fs_tables, &cfg) == cudaSuccess && n2 >= 1)
+                    h->fs_cluster = c;
+            }
+            cudaGetLastError();
+        }
         if (const char* e = getenv("MOT_KEYS_HIST")) h->keys_hist_fused = atoi(e);
         if (const char* e = getenv("MOT_CSR_COMPACT")) h->csr_compact = atoi(e);
         if (const char* e = getenv("MOT_SORT_BITS")) h->rws.digit_bits = std::min(RS_MAX_BITS, std::max(4, atoi(e)));
@@ -942,11 +1230,13 @@ int mot_destroy(mot_handle* h) {
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_offsets_in, h->d_frame_stamps, h->d_c1p_status, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
                     h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
-                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2};
+                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2, h->d_fs_state, h->d_fs_args, h->d_fs_phase_ns};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->h_pinned_fo) cudaFreeHost(h->h_pinned_fo);
+    if (h->h_fs_args) cudaFreeHost(h->h_fs_args);
+    if (h->fs_graph) cudaGraphExecDestroy(h->fs_graph);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : h->timer_ev)
@@ -1010,6 +1300,7 @@ int mot_set_cluster_params(mot_handle* h, float cluster_tolerance, int min_clust
     if (!h) return MOT_ERR_INVALID;
     if (!(cluster_tolerance > 0.0f) || !std::isfinite(cluster_tolerance)) return fail(h, MOT_ERR_INVALID, "cluster_tolerance must be > 0");
     if (min_cluster_size < 1) min_cluster_size = 1;  // PCL: a component always has >= 1 point
+    if (h->tol != cluster_tolerance) h->plan_valid = false;
     h->tol = cluster_tolerance;
     h->min_size = min_cluster_size;
     h->max_size = max_cluster_size;
@@ -1170,11 +1461,10 @@ int mot_cluster(mot_handle* h, const float* xyz16, size_t m, int32_t* cluster_of
     int rc = check_frame_args(h, xyz16, m);
     if (rc != MOT_OK) return rc;
     CK(cudaSetDevice(h->device));
-    rc = reset_frame_state(h);
-    if (rc != MOT_OK) return rc;
+    begin_frame(h);
     CK(cudaEventRecord(h->ev[0], h->stream));
     if (m) CK(cudaMemcpyAsync(h->d_pts, xyz16, m * 16, cudaMemcpyHostToDevice, h->stream));
-    rc = cluster_core(h, h->d_pts, (int)m, 1, false, 0.0);
+    rc = frame_core(h, h->d_pts, (int)m, false, nullptr, false, 0.0);
     if (rc != MOT_OK) return rc;
     if (n_clusters) *n_clusters = h->res_K;
     rc = fetch_result(h, nullptr, 0, cluster_offsets, offsets_capacity, point_indices, indices_capacity, nullptr, nullptr, 0);
@@ -1205,17 +1495,10 @@ int mot_frame_device(mot_handle* h, const float* d_xyz16, size_t n, int do_remov
     if (rc != MOT_OK) return rc;
     if (do_remove_static && !h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
     CK(cudaSetDevice(h->device));
-    rc = reset_frame_state(h);
-    if (rc != MOT_OK) return rc;
+    begin_frame(h);
     CK(cudaEventRecord(h->ev[0], h->stream));
     const float4* src = reinterpret_cast<const float4*>(d_xyz16);
-    if (do_remove_static && n > 0) {
-        rc = enqueue_remove_static(h, src, (int)n, h->d_pts);
-        if (rc != MOT_OK) return rc;
-        rc = cluster_core(h, h->d_pts, -1, 1, with_centroids != 0, stamp);
-    } else {
-        rc = cluster_core(h, do_remove_static ? h->d_pts : src, (int)n, 1, with_centroids != 0, stamp);
-    }
+    rc = frame_core(h, src, (int)n, do_remove_static != 0, h->d_pts, with_centroids != 0, stamp);
     if (rc != MOT_OK) return rc;
     return finish_timings(h);
 }
@@ -1227,17 +1510,10 @@ int mot_frame(mot_handle* h, const float* xyz16, size_t n, double stamp, float* 
     if (rc != MOT_OK) return rc;
     if (!h->have_map) return fail(h, MOT_ERR_NO_MAP, "mot_set_map has not been called");
     CK(cudaSetDevice(h->device));
-    rc = reset_frame_state(h);
-    if (rc != MOT_OK) return rc;
+    begin_frame(h);
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if (n) {
-        CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
-        rc = enqueue_remove_static(h, h->d_in, (int)n, h->d_pts);
-        if (rc != MOT_OK) return rc;
-        rc = cluster_core(h, h->d_pts, -1, 1, centroids_xyzi != nullptr, stamp);
-    } else {
-        rc = cluster_core(h, h->d_pts, 0, 1, centroids_xyzi != nullptr, stamp);
-    }
+    if (n) CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = frame_core(h, h->d_in, (int)n, true, h->d_pts, centroids_xyzi != nullptr, stamp);
     if (rc != MOT_OK) return rc;
     if (m) *m = (size_t)h->res_M;
     if (n_clusters) *n_clusters = h->res_K;
@@ -1269,6 +1545,38 @@ int mot_result_counters(mot_handle* h, int32_t* out, int capacity) {
     if (!h || !out || capacity < 1) return MOT_ERR_INVALID;
     if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
     for (int i = 0; i < capacity; ++i) out[i] = i < CNT_N ? h->res_counters[i] : 0;
+    return MOT_OK;
+}
+
+int mot_grid_plan(mot_handle* h, int enable, int* hits, int* misses) {
+    if (!h) return MOT_ERR_INVALID;
+    if (enable >= 0) {
+        h->plan_spec = enable ? 1 : 0;
+        h->plan_valid = false;
+    }
+    if (hits) *hits = h->plan_hits;
+    if (misses) *misses = h->plan_misses;
+    return MOT_OK;
+}
+
+int mot_small_frames(mot_handle* h, int max_points, int* hits, int* misses) {
+    if (!h) return MOT_ERR_INVALID;
+    if (max_points >= 0) {
+        h->fs_max_points = max_points;
+        h->fs_skip = 0;
+    }
+    if (hits) *hits = h->fs_hits;
+    if (misses) *misses = h->fs_misses;
+    return h->fs_cluster;
+}
+
+int mot_small_frame_phases(mot_handle* h, uint64_t* ns, int capacity) {
+    if (!h || !ns || capacity < 1) return MOT_ERR_INVALID;
+    unsigned long long t[FS_PHASES];
+    CK(cudaSetDevice(h->device));
+    CK(mot_sync(h));
+    CK(cudaMemcpy(t, h->d_fs_phase_ns, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < capacity; ++i) ns[i] = i < FS_PHASES ? (uint64_t)t[i] : 0;
     return MOT_OK;
 }
 
@@ -1526,18 +1834,9 @@ int mot_cluster_pointcloud2(mot_handle* h, const uint8_t* data, size_t n_points,
             warn = rc;
             n = V;
         }
-        rc = reset_bbox(h);
-        if (rc != MOT_OK) return rc;
-        CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), st));
     }
-    if (do_remove_static && n > 0) {  // removeStatic (MOT.cpp:461): d_pts -> d_in
-        rc = enqueue_remove_static(h, h->d_pts, n, h->d_in);
-        if (rc != MOT_OK) return rc;
-        cloud = h->d_in;
-        rc = cluster_core(h, cloud, -1, 1, centroids_xyzi != nullptr, stamp_minus_time_init);
-    } else {
-        rc = cluster_core(h, cloud, n, 1, centroids_xyzi != nullptr, stamp_minus_time_init);
-    }
+    // removeStatic (MOT.cpp:461): d_pts -> d_in, then extract + getCentroid (frame_core clears the counters and the bounding box again)
+    rc = frame_core(h, cloud, n, do_remove_static && n > 0, h->d_in, centroids_xyzi != nullptr, stamp_minus_time_init);
     if (rc != MOT_OK) return rc;
     if (m) *m = (size_t)h->res_M;
     if (n_clusters) *n_clusters = h->res_K;

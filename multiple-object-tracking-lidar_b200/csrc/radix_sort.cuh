@@ -541,7 +541,7 @@ inline RsPlan rs_plan(int n, int key_bits, const RadixWorkspace& ws) {
 template <typename KT>
 __global__ void __launch_bounds__(RS_THREADS) k_cell_keys_hist(const float4* __restrict__ pts, int m, int chunk, GridCodec g,
                                                                 const int* __restrict__ frame_offsets, KT* __restrict__ keys, int bits,
-                                                                unsigned* __restrict__ hist /* [R][G] */) {
+                                                                unsigned* __restrict__ hist /* [R][G] */, int* __restrict__ flags) {
     extern __shared__ unsigned sh_hist[];
     const int R = 1 << bits;
     const unsigned mask = R - 1;
@@ -563,12 +563,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_cell_keys_hist(const float4* __r
             const bool valid = i < end;
             unsigned d = 0xffffffffu;
             if (valid) {
-                int ix = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].x, g.minx), g.inv_e));
-                int iy = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].y, g.miny), g.inv_e));
-                int iz = __double2int_rd(__dmul_rn(__dsub_rn((double)p[j].z, g.minz), g.inv_e));
-                ix = min(max(ix, 0), g.nfx - 1);
-                iy = min(max(iy, 0), g.nfy - 1);
-                iz = min(max(iz, 0), g.nfz - 1);
+                int ix, iy, iz;
+                cell_coords_checked(g, p[j], ix, iy, iz, flags);
                 const int frame = g.n_frames > 1 ? frame_of(frame_offsets, g.n_frames, i) : 0;
                 const KT key = key_compose<KT>(g, frame, ix, iy, iz);
                 keys[i] = key;

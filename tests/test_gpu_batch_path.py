@@ -250,3 +250,77 @@ def test_frame_batch_edge_cases(mot, oracle, synth):
     res = t.frame_batch([empty, empty], do_remove_static=True)
     assert res["K"] == 0 and len(res["indices"]) == 0 and not res["frame_kept_offsets"].any()
     t.close()
+
+
+def _cluster_and_check(t, oracle, cloud, p):
+    off, idx = t.extract(cloud)
+    o_ref, i_ref = oracle.cluster_kdtree(cloud, p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    assert np.array_equal(off, o_ref) and np.array_equal(idx, i_ref)
+    return len(o_ref) - 1
+
+
+@pytest.mark.parametrize("uf_mode", ["1", "2"])
+def test_speculative_grid_plan_hits_and_misses(mot, oracle, synth, monkeypatch, uf_mode):
+    """The handle reuses the grid of its previous call (mot_grid_plan): same extent -> hit, a cloud that grew or moved out of the
+    padded grid -> miss and a second pass from its own bounding box, a different tolerance or frame count -> planned afresh.
+    Every result equals the oracle's, whichever way it was planned."""
+    monkeypatch.setenv("MOT_UF_MODE", uf_mode)
+    p = dict(synth.C1_PARAMS)
+    base, _ = synth.make_frame_c1(n_points=12000)
+    t = mot.Tracker(device=0, max_points=1 << 16, max_tracks=0)
+    t.small_frames(0)   # frames of this size would take the single-launch path, which plans nothing
+    t.set_cluster_params(p["cluster_tolerance"], p["min_cluster_size"], p["max_cluster_size"])
+    assert t.grid_plan() == (0, 0)
+    k0 = _cluster_and_check(t, oracle, base, p)              # first call: planned from the bounding box
+    assert k0 > 0 and t.grid_plan() == (0, 0)
+    _cluster_and_check(t, oracle, base, p)                   # same cloud: hit
+    assert t.grid_plan() == (1, 0)
+    jitter = base.copy()
+    jitter[:, :3] += np.float32(0.01) * np.random.default_rng(3).standard_normal((len(base), 3)).astype(np.float32)
+    _cluster_and_check(t, oracle, jitter, p)                 # a slightly different frame of the same extent: hit
+    assert t.grid_plan() == (2, 0)
+    moved = base.copy()
+    moved[:, 0] += np.float32(500.0)                         # the whole scene far outside the planned grid: miss
+    _cluster_and_check(t, oracle, moved, p)
+    assert t.grid_plan() == (2, 1)
+    _cluster_and_check(t, oracle, moved, p)                  # the miss left a fresh plan behind
+    assert t.grid_plan() == (3, 1)
+    grown = np.concatenate([moved, moved[:50] + np.float32([0, 0, 300.0, 0])])   # one axis outgrows its bits: miss
+    _cluster_and_check(t, oracle, grown, p)
+    assert t.grid_plan() == (3, 2)
+    one = grown.copy()
+    one[7, 1] = np.float32(-1.0e4)                           # a single outlier is enough
+    _cluster_and_check(t, oracle, one, p)
+    assert t.grid_plan()[1] == 3
+    # another tolerance drops the plan (no hit, no miss); a batch call has another frame count (the same)
+    h, m = t.grid_plan()
+    p2 = dict(p, cluster_tolerance=0.2)
+    t.set_cluster_params(p2["cluster_tolerance"], p2["min_cluster_size"], p2["max_cluster_size"])
+    _cluster_and_check(t, oracle, base, p2)
+    assert t.grid_plan() == (h, m)
+    _cluster_and_check(t, oracle, base, p2)
+    assert t.grid_plan() == (h + 1, m)
+    res = t.frame_batch([base, jitter], do_remove_static=False)
+    assert t.grid_plan() == (h + 1, m)
+    res2 = t.frame_batch([base, jitter], do_remove_static=False)
+    assert t.grid_plan() == (h + 2, m)
+    for k in ("offsets", "indices", "frame_cluster_offsets"):
+        assert np.array_equal(res[k], res2[k])
+    res3 = t.frame_batch([moved, jitter], do_remove_static=False)   # batch miss
+    assert t.grid_plan() == (h + 2, m + 1)
+    o_ref, i_ref = oracle.cluster_kdtree(moved, p2["cluster_tolerance"], p2["min_cluster_size"], p2["max_cluster_size"])
+    k1 = res3["frame_cluster_offsets"][1]
+    assert np.array_equal(res3["offsets"][:k1 + 1], o_ref) and np.array_equal(res3["indices"][:o_ref[-1]], i_ref)
+    # NaN under a speculative plan is still the documented error, and the handle works afterwards
+    bad = base.copy()
+    bad[11, 2] = np.nan
+    with pytest.raises(mot.MotError):
+        t.extract(bad)
+    _cluster_and_check(t, oracle, base, p2)
+    # switched off: every call takes its own bounding box, same results
+    t.grid_plan(False)
+    h, m = t.grid_plan()
+    _cluster_and_check(t, oracle, base, p2)
+    _cluster_and_check(t, oracle, base, p2)
+    assert t.grid_plan() == (h, m)
+    t.close()

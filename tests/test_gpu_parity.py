@@ -13,20 +13,26 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5
 
 
-@pytest.fixture(scope="module", params=["cell-path", "auto"])
+@pytest.fixture(scope="module", params=["cell-path", "auto", "small"])
 def trk(mot, request):
-    # every test that takes `trk` runs twice: with the cell-based union-find of round 2 forced (MOT_UF_MODE=2; by default it
-    # only serves calls of >= 1.5 M points) and with the default choice (the round-1 sweep kernels at these sizes)
-    saved = os.environ.get("MOT_UF_MODE")
+    # every test that takes `trk` runs three times: with the cell-based union-find of round 2 forced (MOT_UF_MODE=2; by default
+    # it only serves calls of >= 1.5 M points), with the default choice of the general path (the round-1 sweep kernels at these
+    # sizes) -- both with the single-launch small-frame path switched off --, and with the library's defaults, where single
+    # frames of up to 131,072 points take the small-frame path (k_frame_small) and fall back to the general one when they must
+    saved = {k: os.environ.get(k) for k in ("MOT_UF_MODE", "MOT_SMALL_POINTS")}
     if request.param == "cell-path":
         os.environ["MOT_UF_MODE"] = "2"
+    if request.param != "small":
+        os.environ["MOT_SMALL_POINTS"] = "0"
     try:
-        t = mot.Tracker(device=0, max_points=1 << 21, max_tracks=2048)   # the switch is read by mot_create
+        t = mot.Tracker(device=0, max_points=1 << 21, max_tracks=2048)   # the switches are read by mot_create
     finally:
-        if saved is None:
-            os.environ.pop("MOT_UF_MODE", None)
-        else:
-            os.environ["MOT_UF_MODE"] = saved
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    t.variant = request.param
     yield t
     t.close()
 
@@ -232,13 +238,17 @@ def test_concurrent_handles_on_one_gpu(mot, oracle, synth):
 ALTERNATIVES = [{"MOT_UF_MODE": "2"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0"},
                 {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1", "MOT_UF_PHASES": "7,24"}, {"MOT_UF_MODE": "2", "MOT_UF_FBLOCKS": "2"}, {"MOT_UF_MODE": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_PAIR": "0"}, {"MOT_UF_MODE": "0"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1"}, {"MOT_UF_MODE": "2", "MOT_UF_LIGHT": "1024"},
                 {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0", "MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"}, {"MOT_KEYS_HIST": "1"}, {"MOT_CSR_COMPACT": "0"}, {"MOT_CSR_COMPACT": "8"}, {"MOT_SORT_BIGTILE": "1000"},
-                {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}]
+                {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}, {"MOT_PLAN_SPEC": "0"},
+                {"MOT_SMALL_POINTS": "131072"}, {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CLUSTER": "8"}, {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CLUSTER": "2"},
+                {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CELLCAP": "3"}]
 
 
 @pytest.mark.parametrize("env", ALTERNATIVES, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_alternative_paths_keep_parity(mot, oracle, synth, env):
     # every A/B switch (README) selects a different kernel or host path for the same result: known answers, one LiDAR
     # frame slice with dense and sparse neighbourhoods, one frame batch
+    env = dict(env)
+    env.setdefault("MOT_SMALL_POINTS", "0")   # the switches of the general path are what is under test, unless the entry says otherwise
     saved = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
@@ -274,7 +284,8 @@ def test_alternative_paths_keep_parity(mot, oracle, synth, env):
 def test_u64_key_path_is_taken(trk, oracle):
     pts, tol, mn, mx, _ = kat_cases()["wide_extent_u64_keys"]
     check_extract(trk, oracle, pts, tol, mn, mx)
-    assert trk.result_grid()["key_bits"] > 32
+    if trk.variant != "small":   # (the small-frame path hashes absolute cell coordinates: no sort key at all)
+        assert trk.result_grid()["key_bits"] > 32
     # and in batch mode (frame id in the top key bits)
     trk.set_cluster_params(tol, mn, mx)
     fco, off, idx = trk.extract_batch([pts, pts[::-1].copy(), pts[:500]])
