@@ -41,11 +41,13 @@ constexpr int FS_THREADS = 1024;
 constexpr int FS_MAX_K = 4096;            // clusters the counting rank handles (K^2 comparisons)
 constexpr int FS_MAX_ITEMS = 32;          // input points per thread in the compaction phase (keep bits live in one word)
 enum { FS_ST_T = 0, FS_ST_LOGT = 1, FS_ST_CELLS = 2, FS_ST_EDGES = 3, FS_ST_N = 8 };
+constexpr int FS_MAX_NODES = 49152;       // kept points (= union-find node ids) that fit the shared-memory parent array of k_fs_tables (192 KB)
 constexpr int FS_CELL_RANGE = 1 << 20;    // |cell coordinate| below this (21 bits per axis in the hash key)
 constexpr unsigned long long FS_EMPTY = ~0ull;
 constexpr int FS_FLAG_FALLBACK = 32;      // d_counts[CNT_FLAGS]: the general path has to take this frame
 constexpr int FS_FLAG_NONFINITE = 64;
 constexpr int FS_PHASES = 16;
+constexpr size_t FS_TABLES_SMEM = (size_t)FS_MAX_NODES * 4;  // dynamic shared memory of k_fs_tables (>= (2 FS_MAX_K + 2) ints)
 
 struct FsArgs {
     const float4* src;        // input cloud (device)
@@ -94,6 +96,7 @@ struct FsArgs {
     ClusterStat* stats;         // [K]
     float4* centroids;          // [K]
     int* counts;                // d_counts (CNT_M, CNT_K, CNT_TOTAL, CNT_COARSE, CNT_FLAGS)
+    int* host_counts;           // pinned host copy of the counters, written by the last kernel (zero-copy: no copy node, no extra gap)
     unsigned long long* phase_ns;  // [FS_PHASES] %globaltimer at the end of every phase (thread 0 of CTA 0; diagnostics)
 };
 
@@ -172,18 +175,36 @@ __device__ __forceinline__ unsigned long long fs_block_sum64(unsigned long long 
 // Every CTA publishes `mine`, the cluster barrier makes it visible, every thread reads all of them through DSMEM.
 // Returns the sum over the CTAs ranked before this one in `before` and over all CTAs in `all`.  `slot` must not be reused.
 __device__ __forceinline__ void fs_exchange(cg::cluster_group& cl, FsExchange* slot, const FsExchange& mine, FsExchange& before, FsExchange& all) {
+    __shared__ FsExchange s_before, s_all;
     if (threadIdx.x == 0) *slot = mine;
     cl.sync();
-    before.total = 0; before.cells = 0; before.squares = 0;
-    all = before;
-    const unsigned rank = cl.block_rank(), nb = cl.num_blocks();
-    for (unsigned r = 0; r < nb; ++r) {
-        const FsExchange* remote = cl.map_shared_rank(slot, r);
-        const int t = remote->total, c = remote->cells;
-        const unsigned long long q = remote->squares;
-        if (r < rank) { before.total += t; before.cells += c; before.squares += q; }
-        all.total += t; all.cells += c; all.squares += q;
+    // lane r of the first warp reads CTA r's contribution: the <= 16 remote reads are in flight together (a loop over the CTAs in
+    // every thread serialised 16 x 3 DSMEM round trips, ~2-3 us per exchange)
+    if (threadIdx.x < 32) {
+        const unsigned rank = cl.block_rank(), nb = cl.num_blocks();
+        const unsigned r = threadIdx.x;
+        int t = 0, c = 0;
+        unsigned long long q = 0;
+        if (r < nb) {
+            const FsExchange* remote = cl.map_shared_rank(slot, r);
+            t = remote->total; c = remote->cells; q = remote->squares;
+        }
+        int tb = r < rank ? t : 0, cb = r < rank ? c : 0;
+        unsigned long long qb = r < rank ? q : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(kFull, t, o); c += __shfl_xor_sync(kFull, c, o); q += __shfl_xor_sync(kFull, q, o);
+            tb += __shfl_xor_sync(kFull, tb, o); cb += __shfl_xor_sync(kFull, cb, o); qb += __shfl_xor_sync(kFull, qb, o);
+        }
+        if (threadIdx.x == 0) {
+            s_all.total = t; s_all.cells = c; s_all.squares = q;
+            s_before.total = tb; s_before.cells = cb; s_before.squares = qb;
+        }
     }
+    __syncthreads();
+    before = s_before;
+    all = s_all;
+    __syncthreads();  // s_before / s_all may be rewritten by the next exchange
 }
 
 __device__ __forceinline__ void fs_stamp(const FsArgs& a, int gtid, int phase) {
@@ -207,27 +228,45 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_front(const FsArgs* __rest
     const int NT = nb * FS_THREADS;
     const int gtid = rank * FS_THREADS + tid;
     fs_stamp(a, gtid, 0);
+    if (gtid < CNT_N && gtid != CNT_M) a.counts[gtid] = 0;  // first use is after the next cluster barrier; CNT_M is written below
 
     // ---- A: removeStatic + ordered compaction ---------------------------------------------------------------------------
     const float4* cloud = a.src;
     int M = a.n;
     if (a.do_rs) {
+        // a warp owns 32 * items consecutive points: round k reads points w0 + 32 k + lane (coalesced), four rounds in flight
         const int per_cta = (a.n + nb - 1) / nb;
         const int items = (per_cta + FS_THREADS - 1) / FS_THREADS;  // <= FS_MAX_ITEMS (host)
-        const int cb = rank * per_cta, ce = min(a.n, cb + per_cta);
-        const int i0 = cb + tid * items;
-        unsigned keep = 0;
-        for (int k = 0; k < items; ++k) {
-            const int i = i0 + k;
-            if (i < ce && rs_keep(a.src[i], a.mp, a.bits)) keep |= 1u << k;
+        const int ce = min(a.n, (rank + 1) * per_cta);
+        const int w0 = rank * per_cta + (tid >> 5) * 32 * items;
+        const int lane = tid & 31;
+        unsigned keep = 0;  // bit k: the point of round k
+        for (int k0 = 0; k0 < items; k0 += 4) {
+            float4 p[4];
+            bool in[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = w0 + 32 * (k0 + k) + lane;
+                in[k] = k0 + k < items && i < ce;
+                if (in[k]) p[k] = a.src[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (in[k] && rs_keep(p[k], a.mp, a.bits)) keep |= 1u << (k0 + k);
         }
+        // position of a kept point: CTAs before, warps before (block scan of the warp totals), rounds before, lanes before
+        int warp_total = 0;
+        for (int k = 0; k < items; ++k) warp_total += __popc(__ballot_sync(kFull, (keep >> k) & 1u));
         int cta_total;
-        const int excl = block_exclusive_scan(__popc(keep), sscan, &cta_total);
+        const int warp_excl = block_exclusive_scan(lane == 0 ? warp_total : 0, sscan, &cta_total);
         FsExchange mine{cta_total, 0, 0ull}, before, all;
         fs_exchange(cl, &xch[0], mine, before, all);
-        int pos = before.total + excl;
-        for (int k = 0; k < items; ++k)
-            if ((keep >> k) & 1u) a.kept[pos++] = a.src[i0 + k];
+        int pos = before.total + __shfl_sync(kFull, warp_excl, 0);
+        for (int k = 0; k < items; ++k) {
+            const unsigned m = __ballot_sync(kFull, (keep >> k) & 1u);
+            if ((keep >> k) & 1u) a.kept[pos + __popc(m & lanemask_lt())] = a.src[w0 + 32 * k + lane];
+            pos += __popc(m);
+        }
         M = all.total;
         cloud = a.kept;
     }
@@ -241,14 +280,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_front(const FsArgs* __rest
         a.hstart[s] = 0;
     }
     if (gtid == 0) a.counts[CNT_M] = M;
-    cl.sync();  // kept cloud complete, hash cleared
+    cl.sync();  // kept cloud complete, hash cleared (and the counters, by the first threads)
+    if (M > FS_MAX_NODES) {  // uniform: the shared-memory union-find of k_fs_tables cannot hold the frame
+        if (gtid == 0) atomicOr(a.counts + CNT_FLAGS, FS_FLAG_FALLBACK);
+        return;              // (no shared memory of a neighbour is read after the barrier above)
+    }
     fs_stamp(a, gtid, 1);
 
     // ---- B: fine cell of every point (edge h / 2: a clique), hash insert, rank inside the cell ----------------------------
     for (int i = gtid; i < M; i += NT) {
         const float4 p = cloud[i];
         int cx, cy, cz;
-        a.parent[i] = i;
         a.csize[i] = 0;
         a.cmin[i] = 0x7fffffff;
         a.crank[i] = -1;
@@ -408,41 +450,8 @@ __global__ void __launch_bounds__(FS_PAIR_THREADS) k_fs_edges(const FsArgs* __re
                 const int e = base + __popc(m & lanemask_lt());
                 if (e < a.edge_cap) a.edges[e] = make_int2(lo, hi);
                 else atomicOr(a.counts + CNT_FLAGS, FS_FLAG_FALLBACK);
-                atomicMin(a.parent + hi, lo);
             }
         }
-    }
-}
-
-__global__ void __launch_bounds__(FS_PAIR_THREADS) k_fs_compress(const FsArgs* __restrict__ ap) {
-    const FsArgs a = *ap;
-    const int gtid = blockIdx.x * FS_PAIR_THREADS + threadIdx.x, NT = gridDim.x * FS_PAIR_THREADS;
-    if (a.counts[CNT_FLAGS] != 0) return;
-    const int cells = a.state[FS_ST_CELLS];
-    for (int ci = gtid; ci < cells; ci += NT) {
-        const int x = a.hstart[a.celllist[ci]];
-        int r = ld_cg(a.parent + x);
-        if (r == x) continue;
-        for (;;) {  // parents only decrease: the walk ends at a root of the forest k_fs_edges left
-            const int p = ld_cg(a.parent + r);
-            if (p == r) break;
-            r = p;
-        }
-        st_cg(a.parent + x, r);
-    }
-}
-
-__global__ void __launch_bounds__(FS_PAIR_THREADS) k_fs_link(const FsArgs* __restrict__ ap) {
-    const FsArgs a = *ap;
-    const int gtid = blockIdx.x * FS_PAIR_THREADS + threadIdx.x, NT = gridDim.x * FS_PAIR_THREADS;
-    if (a.counts[CNT_FLAGS] != 0) return;
-    const int n_edges = a.state[FS_ST_EDGES];
-    for (int e = gtid; e < n_edges; e += NT) {
-        const int2 ed = a.edges[e];
-        const int pa = ld_cg(a.parent + ed.x), pb = ld_cg(a.parent + ed.y);
-        if (pa == pb) continue;  // the common case after the compression: both already hang under the same root
-        const int ra = fs_find(a.parent, pa), rb = fs_find(a.parent, pb);
-        if (ra != rb) fs_link(a.parent, ra, rb);
     }
 }
 
@@ -454,7 +463,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
     cg::cluster_group cl = cg::this_cluster();
     __shared__ int sscan[33];
     __shared__ unsigned long long ssum64[32];
-    __shared__ int sbuf[2 * FS_MAX_K + 2];
+    extern __shared__ __align__(16) int dyn[];  // FS_TABLES_SMEM bytes: the parent array first, the cluster tables (sbuf) afterwards
+    int* sbuf = dyn;                            // [2 * FS_MAX_K + 2]
     const int tid = threadIdx.x;
     const int rank = (int)cl.block_rank(), nb = (int)cl.num_blocks();
     const int NT = nb * FS_THREADS;
@@ -464,6 +474,43 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
     if (a.counts[CNT_FLAGS] != 0) return;
     const int M = a.counts[CNT_M];
 
+    // ---- E2: union-find over the listed cell pairs in SHARED memory, by every CTA for itself -------------------------------
+    // The first version joined the cells with finds and CAS in global memory from a wide kernel: every step a dependent L2 round
+    // trip, most of them on the few lines that hold the roots of the large components (ncu: 45-60 % of the stall samples in the
+    // find loops), 20-30 us for 95 k edges.  A small frame's parent array (one int per kept point, node id = cell start) fits the
+    // 192 KB of one CTA, so each CTA of the cluster runs the WHOLE union-find in its own shared memory -- redundantly: 16 x the
+    // edge list out of L2, but no merge, no write-back, ~30-cycle steps -- and flattens its share of the points against it.
+    int* tp = dyn;  // [M]
+    for (int x = tid; x < M; x += FS_THREADS) tp[x] = x;
+    __syncthreads();
+    {
+        const int n_edges = a.state[FS_ST_EDGES];
+        int2 next = tid < n_edges ? a.edges[tid] : make_int2(0, 0);
+        for (int e = tid; e < n_edges; e += FS_THREADS) {
+            const int2 ed = next;
+            if (e + FS_THREADS < n_edges) next = a.edges[e + FS_THREADS];  // in flight while this edge is processed
+            int u = ed.x, v = ed.y;
+            for (;;) {  // lock-free union, both walks in step (two independent shared-memory loads per round); the smaller id stays root
+                const int pu = tp[u], pv = tp[v];
+                if (pu == pv) break;  // same parent: same tree
+                const int gu = tp[pu], gv = tp[pv];
+                if (gu != pu || gv != pv) {  // not both at a root yet: halve the paths and go on
+                    if (gu != pu) tp[u] = gu;
+                    if (gv != pv) tp[v] = gv;
+                    u = gu;
+                    v = gv;
+                    continue;
+                }
+                const int lo = min(pu, pv), hi = max(pu, pv);
+                const int old = atomicCAS(tp + hi, hi, lo);
+                if (old == hi) break;
+                u = old;  // hi had been hooked meanwhile: join where it went
+                v = lo;
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- F: flatten, component size, smallest original index ---------------------------------------------------------------
     const int rounds = (M + NT - 1) / NT;
     for (int it = 0; it < rounds; ++it) {
@@ -471,7 +518,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
         const bool valid = s < M;
         int r = -1, orig = 0x7fffffff;
         if (valid) {
-            r = fs_find(a.parent, a.scell[s]);
+            r = a.scell[s];
+            while (tp[r] != r) r = tp[r];  // (read only: other threads of the CTA are walking too)
             a.root[s] = r;
             orig = __float_as_int(a.spts[s].w);
         }
@@ -585,7 +633,15 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
         const int b0 = soff[lo], b1 = soff[lo + 1];
         const uint32_t v = a.idx_tmp[t];
         int before = 0;
-        for (int u = b0; u < b1; ++u) before += a.idx_tmp[u] < v;
+        // every lane of a warp reads the same addresses (one L1 wavefront per load): four indices per load
+        int u = b0;
+        const int body0 = min(b1, (b0 + 3) & ~3), body1 = max(body0, b1 & ~3);
+        for (; u < body0; ++u) before += a.idx_tmp[u] < v;
+        for (; u < body1; u += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(a.idx_tmp + u);
+            before += (q.x < v) + (q.y < v) + (q.z < v) + (q.w < v);
+        }
+        for (; u < b1; ++u) before += a.idx_tmp[u] < v;
         a.indices[b0 + before] = v;
     }
     fs_stamp(a, gtid, 12);
@@ -660,6 +716,10 @@ __global__ void __launch_bounds__(FS_FIN_THREADS) k_fs_finish(const FsArgs* __re
     __shared__ int sk[FS_FIN_THREADS / 32];
     __shared__ PairCand s2[2];
     fs_stamp(a, blockIdx.x * FS_FIN_THREADS + threadIdx.x, 14);
+    if (blockIdx.x == 0 && threadIdx.x < CNT_N) {  // the counters are final (this kernel changes none of them)
+        a.host_counts[threadIdx.x] = a.counts[threadIdx.x];
+        __threadfence_system();
+    }
     if (a.counts[CNT_FLAGS] != 0) return;
     const int K = a.counts[CNT_K];
     const float4* cloud = a.do_rs ? a.kept : a.src;

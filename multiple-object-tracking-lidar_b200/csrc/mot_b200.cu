@@ -53,7 +53,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_FS_FRONT, KID_FS_EDGES, KID_FS_COMPRESS, KID_FS_LINK, KID_FS_TABLES, KID_FS_FARTHEST, KID_FS_FINISH, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_FS_FRONT, KID_FS_EDGES, KID_FS_TABLES, KID_FS_FARTHEST, KID_FS_FINISH, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -61,7 +61,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build", "k_fs_front", "k_fs_edges", "k_fs_compress", "k_fs_link", "k_fs_tables", "k_fs_farthest", "k_fs_finish"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build", "k_fs_front", "k_fs_edges", "k_fs_tables", "k_fs_farthest", "k_fs_finish"};
 
 struct mot_handle {
     int device = 0;
@@ -823,8 +823,8 @@ int check_frame_args(mot_handle* h, const void* pts, size_t n) {
 
 // Small frames (frame_small.cuh): removeStatic + clustering + tables as five kernels launched back to back -- as ONE
 // instantiated CUDA graph -- with a single host round trip at the end; every size in between (M, cells, K) stays on the device.
-// The kernels of the small-frame path on `st`: counters cleared, arguments copied from their pinned staging, five kernels, counters
-// copied back.  Called directly (profiling / MOT_SMALL_GRAPH=0) or under stream capture (once per handle).
+// The kernels of the small-frame path on `st`: arguments copied from their pinned staging, then the seven kernels (the first
+// clears the counters, the last stores them to pinned host memory).  Called directly (profiling / MOT_SMALL_GRAPH=0) or under stream capture (once per handle).
 int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
     const int wide_grid = h->num_sms * 8;
     cudaLaunchConfig_t cfg = {};
@@ -837,27 +837,25 @@ int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     const FsArgs* ap = h->d_fs_args;
-    CK(cudaMemsetAsync(h->d_counts, 0, CNT_N * sizeof(int), st));
-    CK(cudaMemcpyAsync(h->d_fs_args, h->h_fs_args, sizeof(FsArgs), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_fs_args, h->h_fs_args, sizeof(FsArgs), cudaMemcpyHostToDevice, st));  // (k_fs_front clears the counters)
     if (with_prof) {
         LAUNCH(KID_FS_FRONT, CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap)));
         LAUNCH(KID_FS_EDGES, k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap));
-        LAUNCH(KID_FS_COMPRESS, k_fs_compress<<<h->num_sms, FS_PAIR_THREADS, 0, st>>>(ap));
-        LAUNCH(KID_FS_LINK, k_fs_link<<<wide_grid / 2, FS_PAIR_THREADS, 0, st>>>(ap));
+        cfg.dynamicSmemBytes = FS_TABLES_SMEM;
         LAUNCH(KID_FS_TABLES, CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap)));
-        LAUNCH(KID_FS_FARTHEST, k_fs_farthest<<<wide_grid, FS_FP_THREADS, 0, st>>>(ap));
+        cfg.dynamicSmemBytes = 0;
+        LAUNCH(KID_FS_FARTHEST, k_fs_farthest<<<h->num_sms * 2, FS_FP_THREADS, 0, st>>>(ap));
         LAUNCH(KID_FS_FINISH, k_fs_finish<<<h->num_sms * 2, FS_FIN_THREADS, 0, st>>>(ap));
     } else {
         CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap));
         k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap);
-        k_fs_compress<<<h->num_sms, FS_PAIR_THREADS, 0, st>>>(ap);
-        k_fs_link<<<wide_grid / 2, FS_PAIR_THREADS, 0, st>>>(ap);
+        cfg.dynamicSmemBytes = FS_TABLES_SMEM;
         CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap));
-        k_fs_farthest<<<wide_grid, FS_FP_THREADS, 0, st>>>(ap);
+        cfg.dynamicSmemBytes = 0;
+        k_fs_farthest<<<h->num_sms * 2, FS_FP_THREADS, 0, st>>>(ap);
         k_fs_finish<<<h->num_sms * 2, FS_FIN_THREADS, 0, st>>>(ap);
     }
-    CK(cudaMemcpyAsync(h->h_pinned + 8, h->d_counts, CNT_N * sizeof(int), cudaMemcpyDeviceToHost, st));
-    return MOT_OK;
+    return MOT_OK;  // (k_fs_finish stores the counters to the pinned host copy: no copy node)
 }
 
 int fs_build_graph(mot_handle* h) {
@@ -900,7 +898,7 @@ int frame_small(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_
     a.with_centroids = with_centroids ? 1 : 0;
     a.stamp = (float)stamp;
     a.cell_cap = h->fs_cell_cap;
-    a.fp_ctas = wide_grid;
+    a.fp_ctas = h->num_sms * 2;
     a.order_limit = with_centroids ? (1ull << 22) : (1ull << 25);
     a.log_t = std::max(4, ceil_log2(2 * (long long)n));
     a.T = 1 << a.log_t;  // <= hash_capacity (2^ceil_log2(2 max_points))
@@ -925,6 +923,7 @@ int frame_small(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_
     a.cands = h->d_cands;
     a.labels = h->d_labels; a.cl_offsets = h->d_cl_offsets; a.indices = h->d_vals[0];
     a.stats = h->d_stats; a.centroids = h->d_centroids; a.counts = h->d_counts;
+    a.host_counts = h->h_pinned + 8;
     a.phase_ns = h->d_fs_phase_ns;
     *h->h_fs_args = a;  // the previous call on this handle has been synchronised: the staging is free
     if (h->fs_use_graph && !h->prof.on) {
@@ -935,7 +934,7 @@ int frame_small(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_
     }
     if (h->fs_use_graph && !h->prof.on && h->fs_graph) {
         CK(cudaGraphLaunch(h->fs_graph, st));
-        h->prof.launches += 7;
+        h->prof.launches += 5;
     } else {
         rc = fs_enqueue(h, st, true);
         if (rc != MOT_OK) return rc;
@@ -1143,6 +1142,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
             if (const char* e = getenv("MOT_SMALL_CLUSTER")) want = atoi(e);
             cudaFuncSetAttribute(k_fs_front, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             cudaFuncSetAttribute(k_fs_tables, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(k_fs_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FS_TABLES_SMEM);
             for (int c = want; c >= 1 && h->fs_cluster == 0; c >>= 1) {
                 if (c > 16) continue;
                 cudaLaunchConfig_t cfg = {};
@@ -1156,7 +1156,7 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
                 int n_clusters = 0;
                 int n2 = 0;
                 if (cudaOccupancyMaxActiveClusters(&n_clusters, k_fs_front, &cfg) == cudaSuccess && n_clusters >= 1 &&
-                    cudaOccupancyMaxActiveClusters(&n2, k_fs_tables, &cfg) == cudaSuccess && n2 >= 1)
+                    (cfg.dynamicSmemBytes = FS_TABLES_SMEM, cudaOccupancyMaxActiveClusters(&n2, k_fs_tables, &cfg)) == cudaSuccess && n2 >= 1)
                     h->fs_cluster = c;
             }
             cudaGetLastError();

@@ -40,7 +40,7 @@ def test_c1_frame_takes_the_small_path(mot, oracle, synth):
         cloud, _ = synth.make_frame_c1(frame=f, box_shift=(0.4 * f, -0.3 * f))
         out = _frame_vs_oracle(t, oracle, cloud, occ, resn, origin, p, stamp=0.1 * f)
         assert out["K"] > 0
-        assert t.last_launches() == 7    # front, edges, compress, link, tables, farthest pair, finish -- one graph, one host round trip
+        assert t.last_launches() == 5    # front, cell pairs, tables, farthest pair, finish -- one graph, one host round trip
     assert t.small_frames()[1:] == (4, 0)
     # the same frames through the general path on the same handle: identical arrays
     cloud, _ = synth.make_frame_c1(frame=2)
