@@ -304,12 +304,17 @@ class Tracker:
 
     def small_frame_phases(self):
         """Nanoseconds spent in each phase of the last small-frame launch (dict phase -> ns)."""
-        t = np.zeros(16, dtype=np.uint64)
-        self._ck(self.lib.mot_small_frame_phases(self.h, t, 16))
+        t = np.zeros(32, dtype=np.uint64)
+        self._ck(self.lib.mot_small_frame_phases(self.h, t, 32))
         names = ("front: A rs+compact", "front: B hash insert", "front: C scan", "front: D place", "(gap)", "pairs", "tables: F flatten", "tables: G kept list",
                  "tables: H rank", "tables: I offsets", "tables: J segments", "tables: K order", "(gap)", "farthest pair", "finish")
         t = t.astype(np.int64)
-        return {f"{i:02d} {n}": int(t[i + 1] - t[i]) for i, n in enumerate(names) if t[i + 1] >= t[i] > 0}
+        out = {f"{i:02d} {n}": int(t[i + 1] - t[i]) for i, n in enumerate(names) if t[i + 1] >= t[i] > 0}
+        # sub-steps of the shared-memory union-find inside "tables: F": nanoseconds since the start of k_fs_tables
+        sub = ("forest loaded and flattened", "cell pairs joined", "points flattened")
+        out.update({f"F+ {n}": int(t[16 + i] - t[6]) for i, n in enumerate(sub) if t[16 + i] >= t[6] > 0})
+        out["cell pairs"] = int(t[31])
+        return out
 
     def debug_stats(self):
         """Union-find counters of a -DMOT_UF_STATS build (None for the product build)."""

@@ -46,7 +46,7 @@ constexpr int FS_CELL_RANGE = 1 << 20;    // |cell coordinate| below this (21 bi
 constexpr unsigned long long FS_EMPTY = ~0ull;
 constexpr int FS_FLAG_FALLBACK = 32;      // d_counts[CNT_FLAGS]: the general path has to take this frame
 constexpr int FS_FLAG_NONFINITE = 64;
-constexpr int FS_PHASES = 16;
+constexpr int FS_PHASES = 32;            // 0..15: phase boundaries; 16..: sub-steps of the shared-memory union-find (diagnostics)
 constexpr size_t FS_TABLES_SMEM = (size_t)FS_MAX_NODES * 4;  // dynamic shared memory of k_fs_tables (>= (2 FS_MAX_K + 2) ints)
 
 struct FsArgs {
@@ -74,7 +74,7 @@ struct FsArgs {
     int* scell;                 // [n] start of the placed point's cell
     int* celllist;              // [n] slots of the occupied cells
     float4* fbox;               // [2 n] AABB (lo, hi) of every cell, addressed by cell start
-    int2* edges;                // [edge_cap] confirmed cell pairs (lo, hi)
+    uint32_t* edges;            // [edge_cap] confirmed cell pairs, lo | hi << 16 (node ids < FS_MAX_NODES <= 65536)
     int edge_cap;
     int* state;                 // [FS_ST_N] T, log T, cells of this launch
     int* parent;                // [n]
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_front(const FsArgs* __rest
     for (int i = gtid; i < M; i += NT) {
         const float4 p = cloud[i];
         int cx, cy, cz;
+        a.parent[i] = i;
         a.csize[i] = 0;
         a.cmin[i] = 0x7fffffff;
         a.crank[i] = -1;
@@ -402,7 +403,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_front(const FsArgs* __rest
 // instead of inside the cluster.
 // ======================================================================================================================
 constexpr int FS_PAIR_THREADS = 256;
-__global__ void __launch_bounds__(FS_PAIR_THREADS) k_fs_edges(const FsArgs* __restrict__ ap) {
+constexpr int FS_PAIR_CTAS_PER_SM = 6;  // what 40 registers allow: the grid is one resident wave (a thread per (cell, x-row of five neighbours)
+                                        // with the probes / ranges / boxes of a row requested together was measured too: 30 us instead of 23 --
+                                        // the witness searches of a row then run one after the other; the whole warp on one ambiguous pair at a
+                                        // time: 39 us)
+__global__ void __launch_bounds__(FS_PAIR_THREADS, FS_PAIR_CTAS_PER_SM) k_fs_edges(const FsArgs* __restrict__ ap) {
     const FsArgs a = *ap;
     const int gtid = blockIdx.x * FS_PAIR_THREADS + threadIdx.x, NT = gridDim.x * FS_PAIR_THREADS;
     fs_stamp(a, gtid, 5);
@@ -448,10 +453,32 @@ __global__ void __launch_bounds__(FS_PAIR_THREADS) k_fs_edges(const FsArgs* __re
             base = __shfl_sync(kFull, base, __ffs(m) - 1);
             if (hi >= 0) {
                 const int e = base + __popc(m & lanemask_lt());
-                if (e < a.edge_cap) a.edges[e] = make_int2(lo, hi);
+                if (e < a.edge_cap) a.edges[e] = (uint32_t)lo | ((uint32_t)hi << 16);
                 else atomicOr(a.counts + CNT_FLAGS, FS_FLAG_FALLBACK);
+                atomicMin(a.parent + hi, lo);  // result unused: a reduction, no round trip
             }
         }
+    }
+}
+
+// lock-free union in a shared-memory forest, both walks in step (two independent loads per round); the smaller id stays root
+__device__ __forceinline__ void fs_smem_union(int* tp, int u, int v) {
+    for (;;) {
+        const int pu = tp[u], pv = tp[v];
+        if (pu == pv) return;  // same parent: same tree
+        const int gu = tp[pu], gv = tp[pv];
+        if (gu != pu || gv != pv) {  // not both at a root yet: halve the paths and go on
+            if (gu != pu) tp[u] = gu;
+            if (gv != pv) tp[v] = gv;
+            u = gu;
+            v = gv;
+            continue;
+        }
+        const int lo = min(pu, pv), hi = max(pu, pv);
+        const int old = atomicCAS(tp + hi, hi, lo);
+        if (old == hi) return;
+        u = old;  // hi had been hooked meanwhile: join where it went
+        v = lo;
     }
 }
 
@@ -478,40 +505,52 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
     // The first version joined the cells with finds and CAS in global memory from a wide kernel: every step a dependent L2 round
     // trip, most of them on the few lines that hold the roots of the large components (ncu: 45-60 % of the stall samples in the
     // find loops), 20-30 us for 95 k edges.  A small frame's parent array (one int per kept point, node id = cell start) fits the
-    // 192 KB of one CTA, so each CTA of the cluster runs the WHOLE union-find in its own shared memory -- redundantly: 16 x the
-    // edge list out of L2, but no merge, no write-back, ~30-cycle steps -- and flattens its share of the points against it.
+    // 192 KB of one CTA, so each CTA of the cluster runs the WHOLE union-find in its own shared memory -- redundantly, but with no
+    // merge and ~30-cycle steps -- and flattens its share of the points against it.  (Measured alternative: every CTA joins 1 / nb
+    // of the edges and the forests are merged pairwise through distributed shared memory -- 12-17 us per merge round, 65 us.)
+    // The forest does not start from singletons: k_fs_edges has hooked every cell under its smallest confirmed neighbour
+    // (parent[], one fire-and-forget atomicMin per edge), so after one flattening pass most listed pairs already share a parent
+    // and leave the loop below at its first comparison.
     int* tp = dyn;  // [M]
-    for (int x = tid; x < M; x += FS_THREADS) tp[x] = x;
+    for (int x = tid; x < M; x += FS_THREADS) tp[x] = a.parent[x];
     __syncthreads();
+    for (int x = tid; x < M; x += FS_THREADS) {  // a parent is only ever replaced by an ancestor: concurrent walks stay correct
+        int r = tp[x];
+        if (r == x) continue;
+        while (tp[r] != r) r = tp[r];
+        tp[x] = r;
+    }
+    __syncthreads();
+    fs_stamp(a, gtid, 16);
     {
         const int n_edges = a.state[FS_ST_EDGES];
-        int2 next = tid < n_edges ? a.edges[tid] : make_int2(0, 0);
+        if (gtid == 0) a.phase_ns[FS_PHASES - 1] = (unsigned long long)n_edges;  // (diagnostics: listed cell pairs)
+        const uint32_t* ed = a.edges;
+        uint32_t n0 = tid < n_edges ? ed[tid] : 0u, n1 = tid + FS_THREADS < n_edges ? ed[tid + FS_THREADS] : 0u;
         for (int e = tid; e < n_edges; e += FS_THREADS) {
-            const int2 ed = next;
-            if (e + FS_THREADS < n_edges) next = a.edges[e + FS_THREADS];  // in flight while this edge is processed
-            int u = ed.x, v = ed.y;
-            for (;;) {  // lock-free union, both walks in step (two independent shared-memory loads per round); the smaller id stays root
-                const int pu = tp[u], pv = tp[v];
-                if (pu == pv) break;  // same parent: same tree
-                const int gu = tp[pu], gv = tp[pv];
-                if (gu != pu || gv != pv) {  // not both at a root yet: halve the paths and go on
-                    if (gu != pu) tp[u] = gu;
-                    if (gv != pv) tp[v] = gv;
-                    u = gu;
-                    v = gv;
-                    continue;
-                }
-                const int lo = min(pu, pv), hi = max(pu, pv);
-                const int old = atomicCAS(tp + hi, hi, lo);
-                if (old == hi) break;
-                u = old;  // hi had been hooked meanwhile: join where it went
-                v = lo;
-            }
+            const uint32_t cur = n0;
+            n0 = n1;
+            if (e + 2 * FS_THREADS < n_edges) n1 = ed[e + 2 * FS_THREADS];  // two loads in flight while this edge is processed
+            fs_smem_union(tp, (int)(cur & 0xffffu), (int)(cur >> 16));
         }
         __syncthreads();
     }
+    fs_stamp(a, gtid, 17);
 
     // ---- F: flatten, component size, smallest original index ---------------------------------------------------------------
+    // Sizes and minima are first gathered per CTA in shared memory (behind the parent array, when 3 M ints fit) and flushed with
+    // one global atomic per (CTA, root): thousands of points of one large component otherwise queue up on a single L2 address
+    // (12 us of the 30 this kernel took on a c1 frame).
+    const bool local_acc = 3 * (size_t)M * 4 <= FS_TABLES_SMEM;  // uniform
+    int* scnt = dyn + M;
+    int* smin = dyn + 2 * M;
+    if (local_acc) {
+        for (int x = tid; x < M; x += FS_THREADS) {
+            scnt[x] = 0;
+            smin[x] = 0x7fffffff;
+        }
+        __syncthreads();
+    }
     const int rounds = (M + NT - 1) / NT;
     for (int it = 0; it < rounds; ++it) {
         const int s = it * NT + gtid;
@@ -526,10 +565,26 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fs_tables(const FsArgs* __res
         const unsigned peers = __match_any_sync(kFull, r);
         const int omin = __reduce_min_sync(peers, orig);
         if (valid && lane == __ffs(peers) - 1) {
-            atomicAdd(a.csize + r, __popc(peers));
-            atomicMin(a.cmin + r, omin);
+            if (local_acc) {
+                atomicAdd(scnt + r, __popc(peers));
+                atomicMin(smin + r, omin);
+            } else {
+                atomicAdd(a.csize + r, __popc(peers));
+                atomicMin(a.cmin + r, omin);
+            }
         }
     }
+    if (local_acc) {
+        __syncthreads();
+        for (int x = tid; x < M; x += FS_THREADS) {
+            const int c = scnt[x];
+            if (c > 0) {
+                atomicAdd(a.csize + x, c);
+                atomicMin(a.cmin + x, smin[x]);
+            }
+        }
+    }
+    fs_stamp(a, gtid, 18);
 
     // ---- G: clusters inside [min, max]; labels ---------------------------------------------------------------------------
     cl.sync();

@@ -823,10 +823,9 @@ int check_frame_args(mot_handle* h, const void* pts, size_t n) {
 
 // Small frames (frame_small.cuh): removeStatic + clustering + tables as five kernels launched back to back -- as ONE
 // instantiated CUDA graph -- with a single host round trip at the end; every size in between (M, cells, K) stays on the device.
-// The kernels of the small-frame path on `st`: arguments copied from their pinned staging, then the seven kernels (the first
+// The kernels of the small-frame path on `st`: arguments copied from their pinned staging, then the five kernels (the first
 // clears the counters, the last stores them to pinned host memory).  Called directly (profiling / MOT_SMALL_GRAPH=0) or under stream capture (once per handle).
 int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
-    const int wide_grid = h->num_sms * 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->fs_cluster);
     cfg.blockDim = dim3(FS_THREADS);
@@ -840,7 +839,7 @@ int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
     CK(cudaMemcpyAsync(h->d_fs_args, h->h_fs_args, sizeof(FsArgs), cudaMemcpyHostToDevice, st));  // (k_fs_front clears the counters)
     if (with_prof) {
         LAUNCH(KID_FS_FRONT, CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap)));
-        LAUNCH(KID_FS_EDGES, k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap));
+        LAUNCH(KID_FS_EDGES, k_fs_edges<<<h->num_sms * FS_PAIR_CTAS_PER_SM, FS_PAIR_THREADS, 0, st>>>(ap));
         cfg.dynamicSmemBytes = FS_TABLES_SMEM;
         LAUNCH(KID_FS_TABLES, CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap)));
         cfg.dynamicSmemBytes = 0;
@@ -848,7 +847,7 @@ int fs_enqueue(mot_handle* h, cudaStream_t st, bool with_prof) {
         LAUNCH(KID_FS_FINISH, k_fs_finish<<<h->num_sms * 2, FS_FIN_THREADS, 0, st>>>(ap));
     } else {
         CK(cudaLaunchKernelEx(&cfg, k_fs_front, ap));
-        k_fs_edges<<<wide_grid, FS_PAIR_THREADS, 0, st>>>(ap);
+        k_fs_edges<<<h->num_sms * FS_PAIR_CTAS_PER_SM, FS_PAIR_THREADS, 0, st>>>(ap);
         cfg.dynamicSmemBytes = FS_TABLES_SMEM;
         CK(cudaLaunchKernelEx(&cfg, k_fs_tables, ap));
         cfg.dynamicSmemBytes = 0;
@@ -909,8 +908,8 @@ int frame_small(mot_handle* h, const float4* src, int n, bool do_rs, float4* rs_
     a.spts = h->d_spts;
     a.scell = reinterpret_cast<int*>(h->d_croots[1]);
     a.celllist = reinterpret_cast<int*>(h->d_crec);
-    a.edges = reinterpret_cast<int2*>(h->d_nbr);
-    a.edge_cap = (int)std::min<size_t>(h->max_points * 8, 0x7fffffff);
+    a.edges = reinterpret_cast<uint32_t*>(h->d_nbr);
+    a.edge_cap = (int)std::min<size_t>(h->max_points * 16, 0x7fffffff);
     a.fbox = h->d_fbox;
     a.state = h->d_fs_state;
     a.parent = h->d_parent; a.root = h->d_root; a.csize = h->d_csize; a.cmin = h->d_cmin; a.crank = h->d_crank;

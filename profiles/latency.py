@@ -45,5 +45,5 @@ for name, cloud, p, full in cases:
         med, best = wall_us(lambda: trk.frame_device(d.data_ptr(), len(cloud), full, full, 1.0))
         print(f"{name:66s} plan_spec={int(spec)}  median {med:7.1f} us  min {best:7.1f} us  launches {trk.last_launches()}  hits/misses {trk.grid_plan()}")
     if trk.last_launches() <= 7:
-        print("    small-frame phases (us):", {k: round(v / 1e3, 1) for k, v in trk.small_frame_phases().items()}, trk.small_frames(), trk.result_counts())
+        print("    small-frame phases (us):", {k: round(v / 1e3, 1) for k, v in trk.small_frame_phases().items()}, trk.small_frames(), trk.result_counts(), trk.result_grid())
     trk.close()
