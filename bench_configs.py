@@ -90,20 +90,28 @@ def run(mot, oracle, device, peak, quick=False):
     d_cloud = torch.from_numpy(cloud).to(dev)
     ms_dev = _median_ms(trk, lambda: trk.frame_device(d_cloud.data_ptr(), len(cloud), True, True, 1.0), reps=15)
     launches = trk.last_launches()
-    ms_host = _median_ms(trk, lambda: trk.frame(cloud, 1.0), reps=9)
+    bufs = trk.frame_buffers(len(cloud))  # caller-owned output buffers, as a C++ caller of mot_frame keeps them (pageable memory)
+    ms_host = _median_ms(trk, lambda: trk.frame_into(cloud, bufs, 1.0), reps=15, warm=3)
     g = trk.result_grid()
+    ph = trk.small_frame_phases() if launches <= 5 else {}
+    dev_us = round(sum(v for k, v in ph.items() if k[:2].isdigit()) / 1e3, 1) if ph else None
     b1 = _frame_bytes(len(cloud), o1["m"], g["coarse_cells"], o1["K"], g["key_bits"])
     out["c1"] = _entry(len(cloud), ms_dev, b1, peak, ok1, call="mot_frame_device (removeStatic + clustering + tables + circumcentres)",
                        kept=int(o1["m"]), clusters=int(o1["K"]), launches=launches, host_buffers_ms=round(ms_host, 4),
-                       roofline_us=round(b1 / (peak * 1e9) * 1e6, 2))
+                       roofline_us=round(b1 / (peak * 1e9) * 1e6, 2),
+                       path="small-frame path: one CUDA graph of 5 kernels, one host round trip" if launches <= 5 else "general path",
+                       device_us=dev_us, timing="ms: CUDA events around the call (launch + kernels + the wait); device_us: first to last kernel "
+                       "instruction (%globaltimer stamps); host_buffers_ms: mot_frame with pageable caller-owned buffers, copies included")
     trk.set_profiling(True)
     reps = 5
     for _ in range(reps):
         trk.frame_device(d_cloud.data_ptr(), len(cloud), True, True, 1.0)
     prof = trk.profile()
     trk.set_profiling(False)
-    kernels += _kernel_rows(prof, reps, ("k_compact_onepass<map>", "k_farthest_pair", "k_circumcentre"),
-                            {"k_compact_onepass<map>": 16 * len(cloud) + 16 * o1["m"], "k_circumcentre": 16 * int(off_ref[-1]) + 16 * o1["K"]}, peak)
+    kernels += _kernel_rows(prof, reps, ("k_compact_onepass<map>", "k_farthest_pair", "k_circumcentre", "k_fs_front", "k_fs_edges", "k_fs_tables",
+                                         "k_fs_farthest", "k_fs_finish"),
+                            {"k_compact_onepass<map>": 16 * len(cloud) + 16 * o1["m"], "k_circumcentre": 16 * int(off_ref[-1]) + 16 * o1["K"],
+                             "k_fs_front": 16 * len(cloud) + 100 * o1["m"]}, peak)
 
     # ---- c5: tracker step = the c1 frame through the host-buffer call + IHGP for 1,000 tracks (L = 40) ----------------------
     T, L = 1000, 40
@@ -117,7 +125,7 @@ def run(mot, oracle, device, peak, quick=False):
     ok5 = ok1 and np.allclose(pv, pv_ref, rtol=1e-5, atol=1e-6) and np.allclose(m_gpu, m_ref, rtol=1e-5, atol=1e-9)
 
     def step_c5():
-        trk.frame(cloud, 1.0)
+        trk.frame_into(cloud, bufs, 1.0)
         trk.ihgp_step(rings, m_gpu)
 
     ms5 = _median_ms(trk, step_c5, reps=9)

@@ -268,6 +268,22 @@ class Tracker:
         return dict(m=M, K=K, kept=kept[:M] if want_kept else None, offsets=off[: K + 1].copy(), indices=idx[: off[K]].copy(),
                     stats=st[:K].copy() if want_stats else None, centroids=cen[:K].copy() if want_centroids else None)
 
+    def frame_buffers(self, n):
+        """Caller-owned output buffers for frame_into(), allocated (and touched) once -- what a C++ caller of mot_frame keeps."""
+        return dict(n=int(n), kept=np.zeros((n, 4), dtype=np.float32), off=np.zeros(n + 1, dtype=np.int32), idx=np.zeros(max(n, 1), dtype=np.int32),
+                    st=np.zeros(max(n, 1), dtype=STAT_DTYPE), cen=np.zeros((max(n, 1), 4), dtype=np.float32))
+
+    def frame_into(self, cloud, bufs, stamp_minus_time_init=0.0):
+        """mot_frame into preallocated buffers (no allocation, no copies of the results): returns (M, K); the arrays of `bufs` hold
+        kept[:M], off[:K + 1], idx[:off[K]], st[:K], cen[:K]."""
+        n = len(cloud)
+        assert n <= bufs["n"] and cloud.dtype == np.float32 and cloud.flags.c_contiguous
+        m = _SIZE(0)
+        k = C.c_int32(0)
+        self._ck(self.lib.mot_frame(self.h, _ptr(cloud), n, float(stamp_minus_time_init), _ptr(bufs["kept"]), bufs["n"], C.byref(m), _ptr(bufs["off"]),
+                                    len(bufs["off"]), _ptr(bufs["idx"]), len(bufs["idx"]), C.byref(k), _ptr(bufs["st"]), _ptr(bufs["cen"]), len(bufs["st"])))
+        return m.value, k.value
+
     # -- device-resident path ------------------------------------------------------------------------------
     def frame_device(self, d_ptr, n, do_remove_static=False, with_centroids=False, stamp_minus_time_init=0.0):
         self._ck(self.lib.mot_frame_device(self.h, C.c_void_p(int(d_ptr)), int(n), int(do_remove_static), int(with_centroids),

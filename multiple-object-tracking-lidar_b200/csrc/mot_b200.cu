@@ -175,6 +175,10 @@ struct mot_handle {
     size_t table_capacity = 0, cand_capacity = 0;
     int* h_pinned = nullptr;  // 32 ints: counts + bbox readback
     int* h_pinned_fo = nullptr;  // pinned staging of a batch's frame offsets (+ stamps)
+    // small transfers between PAGEABLE caller buffers and the device go through pinned staging: a pageable cudaMemcpyAsync is a
+    // synchronous driver call (~20-60 us each; the one-frame host entry makes six of them), pinned copies are queued in ~2 us
+    unsigned char* h_stage = nullptr;  // [STAGE_IN + STAGE_OUT]
+    int stage_on = 1;                  // MOT_HOST_STAGE=0: every copy goes straight to / from the caller's pointer
 
     // IHGP
     bool ihgp_ready = false;
@@ -784,31 +788,79 @@ int finish_timings(mot_handle* h) {
     return MOT_OK;
 }
 
+constexpr size_t STAGE_IN = 2u << 20, STAGE_OUT = 2u << 20, STAGE_CHUNK = 256u << 10;
+
+// true for ordinary (pageable, unregistered) host memory; pinned, managed and device pointers take the direct copies
+bool is_pageable_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// caller's cloud -> device (stream ordered).  A small pageable source is copied chunk by chunk into the pinned staging, every chunk's DMA
+// running while the next one is copied; the staging is free again when the call has synchronised (every host entry does).
+int upload_cloud(mot_handle* h, void* d_dst, const void* src, size_t bytes) {
+    if (!bytes) return MOT_OK;
+    if (h->h_stage && bytes <= STAGE_IN && is_pageable_host(src)) {
+        for (size_t o = 0; o < bytes; o += STAGE_CHUNK) {
+            const size_t c = std::min(STAGE_CHUNK, bytes - o);
+            std::memcpy(h->h_stage + o, static_cast<const unsigned char*>(src) + o, c);
+            CK(cudaMemcpyAsync(static_cast<unsigned char*>(d_dst) + o, h->h_stage + o, c, cudaMemcpyHostToDevice, h->stream));
+        }
+        return MOT_OK;
+    }
+    CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyDefault, h->stream));
+    return MOT_OK;
+}
+
 int fetch_result(mot_handle* h, float* kept, size_t kept_cap, int32_t* offs, size_t offs_cap, int32_t* idx, size_t idx_cap,
                  mot_cluster_stat* stats, float* cent, size_t table_cap) {
     if (!h->have_result) return fail(h, MOT_ERR_STATE, "no clustering result on this handle");
     cudaStream_t st = h->stream;
-    if (kept) {
-        if (kept_cap < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "kept cloud buffer too small");
-        if (h->res_M) CK(cudaMemcpyAsync(kept, h->res_cloud, (size_t)h->res_M * 16, cudaMemcpyDefault, st));
-    }
-    if (offs) {
-        if (offs_cap < (size_t)h->res_K + 1) return fail(h, MOT_ERR_CAPACITY, "cluster_offsets buffer too small");
-        CK(cudaMemcpyAsync(offs, h->d_cl_offsets, ((size_t)h->res_K + 1) * 4, cudaMemcpyDefault, st));
-    }
-    if (idx) {
-        if (idx_cap < (size_t)h->res_total) return fail(h, MOT_ERR_CAPACITY, "point_indices buffer too small");
-        if (h->res_total) CK(cudaMemcpyAsync(idx, h->d_vals[h->res_idx_buf], (size_t)h->res_total * 4, cudaMemcpyDefault, st));
-    }
-    if (stats && h->res_K) {
-        if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "stats buffer too small");
-        CK(cudaMemcpyAsync(stats, h->d_stats, (size_t)h->res_K * sizeof(ClusterStat), cudaMemcpyDefault, st));
-    }
+    if (kept && kept_cap < (size_t)h->res_M) return fail(h, MOT_ERR_CAPACITY, "kept cloud buffer too small");
+    if (offs && offs_cap < (size_t)h->res_K + 1) return fail(h, MOT_ERR_CAPACITY, "cluster_offsets buffer too small");
+    if (idx && idx_cap < (size_t)h->res_total) return fail(h, MOT_ERR_CAPACITY, "point_indices buffer too small");
+    if (stats && h->res_K && table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "stats buffer too small");
     if (cent && h->res_K) {
         if (table_cap < (size_t)h->res_K) return fail(h, MOT_ERR_CAPACITY, "centroid buffer too small");
         if (!h->res_centroids) return fail(h, MOT_ERR_STATE, "centroids were not computed for the last result");
-        CK(cudaMemcpyAsync(cent, h->d_centroids, (size_t)h->res_K * 16, cudaMemcpyDefault, st));
     }
+    struct Part { void* dst; const void* src; size_t bytes; };
+    const Part parts[5] = {
+        {kept, h->res_cloud, kept ? (size_t)h->res_M * 16 : 0},
+        {offs, h->d_cl_offsets, offs ? ((size_t)h->res_K + 1) * 4 : 0},
+        {idx, h->d_vals[h->res_idx_buf], idx ? (size_t)h->res_total * 4 : 0},
+        {stats, h->d_stats, stats ? (size_t)h->res_K * sizeof(ClusterStat) : 0},
+        {cent, h->d_centroids, cent ? (size_t)h->res_K * 16 : 0}};
+    size_t total = 0;
+    bool stage = h->h_stage != nullptr;
+    for (const Part& p : parts)
+        if (p.bytes) {
+            total += (p.bytes + 63) & ~(size_t)63;
+            stage = stage && total <= STAGE_OUT && is_pageable_host(p.dst);
+        }
+    if (stage && total) {  // all parts into the pinned staging (queued back to back), one wait, then plain copies to the caller's buffers
+        unsigned char* out = h->h_stage + STAGE_IN;
+        size_t o = 0;
+        for (const Part& p : parts)
+            if (p.bytes) {
+                CK(cudaMemcpyAsync(out + o, p.src, p.bytes, cudaMemcpyDeviceToHost, st));
+                o += (p.bytes + 63) & ~(size_t)63;
+            }
+        CK(mot_sync(h));
+        o = 0;
+        for (const Part& p : parts)
+            if (p.bytes) {
+                std::memcpy(p.dst, out + o, p.bytes);
+                o += (p.bytes + 63) & ~(size_t)63;
+            }
+        return MOT_OK;
+    }
+    for (const Part& p : parts)
+        if (p.bytes) CK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDefault, st));
     CK(mot_sync(h));
     return MOT_OK;
 }
@@ -1166,6 +1218,8 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
         CK(dalloc(&h->d_blk, (size_t)32 * 1024));
         CK(dalloc(&h->d_bbox, (size_t)8));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned), 64 * sizeof(int), cudaHostAllocDefault));
+        if (const char* e = getenv("MOT_HOST_STAGE")) h->stage_on = atoi(e);
+        if (h->stage_on) CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_stage), STAGE_IN + STAGE_OUT, cudaHostAllocDefault));
         h->frame_capacity = 4096;
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_pinned_fo), (2 * h->frame_capacity + 8) * sizeof(int), cudaHostAllocDefault));
         CK(dalloc(&h->d_frame_offsets, h->frame_capacity + 2));
@@ -1233,6 +1287,7 @@ int mot_destroy(mot_handle* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_pinned_fo) cudaFreeHost(h->h_pinned_fo);
     if (h->h_fs_args) cudaFreeHost(h->h_fs_args);
     if (h->fs_graph) cudaGraphExecDestroy(h->fs_graph);
@@ -1462,7 +1517,8 @@ int mot_cluster(mot_handle* h, const float* xyz16, size_t m, int32_t* cluster_of
     CK(cudaSetDevice(h->device));
     begin_frame(h);
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if (m) CK(cudaMemcpyAsync(h->d_pts, xyz16, m * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = upload_cloud(h, h->d_pts, xyz16, m * 16);
+    if (rc != MOT_OK) return rc;
     rc = frame_core(h, h->d_pts, (int)m, false, nullptr, false, 0.0);
     if (rc != MOT_OK) return rc;
     if (n_clusters) *n_clusters = h->res_K;
@@ -1511,7 +1567,8 @@ int mot_frame(mot_handle* h, const float* xyz16, size_t n, double stamp, float* 
     CK(cudaSetDevice(h->device));
     begin_frame(h);
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if (n) CK(cudaMemcpyAsync(h->d_in, xyz16, n * 16, cudaMemcpyHostToDevice, h->stream));
+    rc = upload_cloud(h, h->d_in, xyz16, n * 16);
+    if (rc != MOT_OK) return rc;
     rc = frame_core(h, h->d_in, (int)n, true, h->d_pts, centroids_xyzi != nullptr, stamp);
     if (rc != MOT_OK) return rc;
     if (m) *m = (size_t)h->res_M;

@@ -240,7 +240,7 @@ ALTERNATIVES = [{"MOT_UF_MODE": "2"}, {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "1"},
                 {"MOT_UF_MODE": "2", "MOT_UF_XMODE": "0", "MOT_UF_SPLIT": "1"}, {"MOT_UF_MODE": "1", "MOT_UF_BLOCKS": "3"}, {"MOT_UF_MODE": "1", "MOT_UF_TMA": "0"}, {"MOT_SORT_MODE": "1"}, {"MOT_SORT_BITS": "8"}, {"MOT_KEYS_HIST": "1"}, {"MOT_CSR_COMPACT": "0"}, {"MOT_CSR_COMPACT": "8"}, {"MOT_SORT_BIGTILE": "1000"},
                 {"MOT_UF_PRIO": "0"}, {"MOT_SYNC": "yield"}, {"MOT_SYNC": "block"}, {"MOT_PLAN_SPEC": "0"},
                 {"MOT_SMALL_POINTS": "131072"}, {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CLUSTER": "8"}, {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CLUSTER": "2"},
-                {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CELLCAP": "3"}]
+                {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_CELLCAP": "3"}, {"MOT_HOST_STAGE": "0"}, {"MOT_SMALL_POINTS": "131072", "MOT_SMALL_GRAPH": "0"}]
 
 
 @pytest.mark.parametrize("env", ALTERNATIVES, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
