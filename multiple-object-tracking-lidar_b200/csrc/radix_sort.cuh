@@ -95,13 +95,23 @@ __global__ void __launch_bounds__(256) k_rs_scan(const unsigned* __restrict__ hi
     if (lane == 0) tot[d] = run;
 }
 
-constexpr int RS_ITEMS_BIG = 32;  // 8192-pair tiles for large inputs: 4x longer digit runs per tile (fewer partial sectors at L2)
+#ifndef RS_ITEMS_BIG_V
+#define RS_ITEMS_BIG_V 32
+#endif
+constexpr int RS_ITEMS_BIG = RS_ITEMS_BIG_V;  // 8192-pair tiles for large inputs: 4x longer digit runs per tile (fewer partial sectors at L2)
+#ifndef RS_SCATTER_CTAS_BIG
+#define RS_SCATTER_CTAS_BIG 2
+#endif
+// shared memory of the scatter: tile_off[R], gbase[R], scan scratch, then ONE region that first holds the per-warp digit counters
+// and, once every pair knows its slot, the re-ordered tile (the counters are dead by then): 72 KB instead of 106 KB at 8192 pairs,
+// so three CTAs fit an SM instead of two
 constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes, int items = RS_ITEMS) {
-    return (size_t)(RS_WARPS + 2) * ((size_t)1 << bits) * 4 + 36 * 4 + (size_t)RS_THREADS * items * 4 + (size_t)RS_THREADS * items * key_bytes;
+    const size_t cnt = (size_t)RS_WARPS * ((size_t)1 << bits) * 4, tile = (size_t)RS_THREADS * items * (4 + key_bytes);
+    return 2 * ((size_t)1 << bits) * 4 + 36 * 4 + (cnt > tile ? cnt : tile);
 }
 
 template <typename KT, bool IOTA, int ITEMS = RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, ITEMS >= 32 ? (sizeof(KT) == 4 ? RS_SCATTER_CTAS_BIG : 2) : 4) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                             KT* __restrict__ kout, uint32_t* __restrict__ vout, int n, int chunk,
                                                             int shift, int bits, const unsigned* __restrict__ prefix,
                                                             const unsigned* __restrict__ tot) {
@@ -109,12 +119,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
     constexpr int TILE = RS_THREADS * ITEMS;
     const int R = 1 << bits;
     const unsigned mask = R - 1;
-    unsigned* cnt = reinterpret_cast<unsigned*>(rs_smem);  // [RS_WARPS][R]
-    unsigned* tile_off = cnt + RS_WARPS * R;               // [R]
-    unsigned* gbase = tile_off + R;                        // [R]
-    int* scan_tmp = reinterpret_cast<int*>(gbase + R);     // [36]
-    uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 36);
-    KT* st_keys = reinterpret_cast<KT*>(st_vals + TILE);
+    unsigned* tile_off = reinterpret_cast<unsigned*>(rs_smem);  // [R]
+    unsigned* gbase = tile_off + R;                             // [R]
+    int* scan_tmp = reinterpret_cast<int*>(gbase + R);          // [36]
+    unsigned* cnt = reinterpret_cast<unsigned*>(scan_tmp + 36);  // [RS_WARPS][R]   -- the same bytes as --
+    uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 36);  // [TILE]
+    KT* st_keys = reinterpret_cast<KT*>(st_vals + TILE);             // [TILE]
 
     const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const int G = gridDim.x, b = blockIdx.x;
@@ -143,22 +153,51 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
     const int begin = b * chunk;
     const int end = min(n, begin + chunk);
     for (int tile_begin = begin; tile_begin < end; tile_begin += TILE) {
-        for (int i = tid; i < RS_WARPS * R; i += RS_THREADS) cnt[i] = 0;
+        {   // clear the counters (the previous tile's write-out has been fenced by the barrier that ends the loop body)
+            uint4* c4 = reinterpret_cast<uint4*>(cnt);
+            for (int i = tid; i < RS_WARPS * R / 4; i += RS_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (R < 4)
+                for (int i = tid; i < RS_WARPS * R; i += RS_THREADS) cnt[i] = 0;
+        }
         __syncthreads();
 
         KT key[ITEMS];
-        uint32_t val[ITEMS];
-        unsigned rank[ITEMS];
+        unsigned rank[ITEMS / 2];  // two 16-bit slots per register (a slot is < TILE <= 65536)
+        static_assert(ITEMS % 8 == 0 && RS_THREADS * ITEMS <= 65536, "packed ranks, batches of eight");
         const int seg = tile_begin + w * (32 * ITEMS);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
-            const bool valid = idx < end;
-            key[i] = valid ? kin[idx] : ~(KT)0;
-            if (IOTA) val[i] = (uint32_t)idx;
-            else val[i] = valid ? vin[idx] : 0u;
+            key[i] = idx < end ? kin[idx] : ~(KT)0;
         }
         unsigned* wcnt = cnt + w * R;
+#ifndef RS_RANK_LDST
+        // Rank inside the warp: match.any groups the lanes with equal digits, the group's first lane bumps the warp's counter with ONE
+        // shared-memory atomic.  Eight items are in flight: the atomics of a batch are issued back to back (the counter update of
+        // item i+1 does not wait for the value item i got back, as the load / add / store version did -- the loop was one long
+        // dependency chain through shared memory), their results are collected afterwards.  Atomics of one warp on one address
+        // are applied in program order (__syncwarp between them), so the ranks stay stable.
+#pragma unroll
+        for (int i0 = 0; i0 < ITEMS; i0 += 8) {
+            unsigned peers[8], old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = seg + (i0 + j) * 32 + lane;
+                const unsigned d = idx < end ? (unsigned)((key[i0 + j] >> shift) & mask) : mask;  // padding sorts last
+                peers[j] = __match_any_sync(kFull, d);
+                old[j] = 0;
+                if (lane == __ffs(peers[j]) - 1) old[j] = atomicAdd(wcnt + d, (unsigned)__popc(peers[j]));
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j;
+                const unsigned r = __shfl_sync(kFull, old[j], __ffs(peers[j]) - 1) + (unsigned)__popc(peers[j] & lanemask_lt());
+                if (i & 1) rank[i / 2] |= r << 16;
+                else rank[i / 2] = r;
+            }
+        }
+#else
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
@@ -171,9 +210,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
                 wcnt[d] = old + (unsigned)__popc(peers);
             }
             old = __shfl_sync(kFull, old, leader);
-            rank[i] = old + (unsigned)__popc(peers & lanemask_lt());
+            const unsigned r = old + (unsigned)__popc(peers & lanemask_lt());
+            if (i & 1) rank[i / 2] |= r << 16;
+            else rank[i / 2] = r;
             __syncwarp();
         }
+#endif
         __syncthreads();
 
         // per digit: exclusive prefix over the warps; tile_off[d] temporarily holds the tile's digit count
@@ -210,13 +252,20 @@ __global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const KT* __restrict_
         }
         __syncthreads();
 
+        // slot of every pair inside the re-ordered tile; after the barrier the counters are dead and their bytes take the tile
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int idx = seg + i * 32 + lane;
             const unsigned d = idx < end ? (unsigned)((key[i] >> shift) & mask) : mask;
-            const unsigned pos = tile_off[d] + wcnt[d] + rank[i];
-            st_keys[pos] = key[i];
-            st_vals[pos] = val[i];
+            rank[i / 2] += (tile_off[d] + wcnt[d]) << (16 * (i & 1));  // (no carry out of a half: the sum is a slot of this tile)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int idx = seg + i * 32 + lane;
+            const unsigned slot = (rank[i / 2] >> (16 * (i & 1))) & 0xffffu;
+            st_keys[slot] = key[i];
+            st_vals[slot] = IOTA ? (uint32_t)idx : (idx < end ? vin[idx] : 0u);  // (values are only read now: they never sat in registers beside keys and ranks)
         }
         __syncthreads();
 
