@@ -95,40 +95,43 @@ __global__ void __launch_bounds__(256) k_rs_scan(const unsigned* __restrict__ hi
     if (lane == 0) tot[d] = run;
 }
 
-#ifndef RS_ITEMS_BIG_V
-#define RS_ITEMS_BIG_V 32
+#ifndef RS_BIG_THREADS_V
+#define RS_BIG_THREADS_V 512
 #endif
-constexpr int RS_ITEMS_BIG = RS_ITEMS_BIG_V;  // 8192-pair tiles for large inputs: 4x longer digit runs per tile (fewer partial sectors at L2)
+constexpr int RS_BIG_THREADS = RS_BIG_THREADS_V;   // CTA width of the scatter on large inputs
+constexpr int RS_BIG_TILE = 8192;                  // pairs per tile there: 4x longer digit runs per tile (fewer partial sectors at L2)
+constexpr int RS_ITEMS_BIG = RS_BIG_TILE / RS_BIG_THREADS;
 #ifndef RS_SCATTER_CTAS_BIG
 #define RS_SCATTER_CTAS_BIG 2
 #endif
 // shared memory of the scatter: tile_off[R], gbase[R], scan scratch, then ONE region that first holds the per-warp digit counters
 // and, once every pair knows its slot, the re-ordered tile (the counters are dead by then): 72 KB instead of 106 KB at 8192 pairs,
 // so three CTAs fit an SM instead of two
-constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes, int items = RS_ITEMS) {
-    const size_t cnt = (size_t)RS_WARPS * ((size_t)1 << bits) * 4, tile = (size_t)RS_THREADS * items * (4 + key_bytes);
+constexpr size_t rs_scatter_smem_bytes(int bits, size_t key_bytes, int items = RS_ITEMS, int threads = RS_THREADS) {
+    const size_t cnt = (size_t)(threads / 32) * ((size_t)1 << bits) * 4, tile = (size_t)threads * items * (4 + key_bytes);
     return 2 * ((size_t)1 << bits) * 4 + 36 * 4 + (cnt > tile ? cnt : tile);
 }
 
-template <typename KT, bool IOTA, int ITEMS = RS_ITEMS>
-__global__ void __launch_bounds__(RS_THREADS, ITEMS >= 32 ? (sizeof(KT) == 4 ? RS_SCATTER_CTAS_BIG : 2) : 4) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
+template <typename KT, bool IOTA, int ITEMS = RS_ITEMS, int THREADS = RS_THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS * ITEMS >= RS_BIG_TILE ? RS_SCATTER_CTAS_BIG : 4) k_rs_scatter(const KT* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                             KT* __restrict__ kout, uint32_t* __restrict__ vout, int n, int chunk,
                                                             int shift, int bits, const unsigned* __restrict__ prefix,
                                                             const unsigned* __restrict__ tot) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    constexpr int TILE = RS_THREADS * ITEMS;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
     const int R = 1 << bits;
     const unsigned mask = R - 1;
     unsigned* tile_off = reinterpret_cast<unsigned*>(rs_smem);  // [R]
     unsigned* gbase = tile_off + R;                             // [R]
     int* scan_tmp = reinterpret_cast<int*>(gbase + R);          // [36]
-    unsigned* cnt = reinterpret_cast<unsigned*>(scan_tmp + 36);  // [RS_WARPS][R]   -- the same bytes as --
+    unsigned* cnt = reinterpret_cast<unsigned*>(scan_tmp + 36);  // [WARPS][R]   -- the same bytes as --
     uint32_t* st_vals = reinterpret_cast<uint32_t*>(scan_tmp + 36);  // [TILE]
     KT* st_keys = reinterpret_cast<KT*>(st_vals + TILE);             // [TILE]
 
     const int tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const int G = gridDim.x, b = blockIdx.x;
-    const int per = (R + RS_THREADS - 1) / RS_THREADS;  // digits owned by a thread (<= 4)
+    const int per = (R + THREADS - 1) / THREADS;  // digits owned by a thread (<= 4)
     const int d0 = tid * per;
 
     // gbase[d] = (exclusive scan of tot over digits)[d] + prefix[d][b]
@@ -155,15 +158,15 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS >= 32 ? (sizeof(KT) == 4 ? R
     for (int tile_begin = begin; tile_begin < end; tile_begin += TILE) {
         {   // clear the counters (the previous tile's write-out has been fenced by the barrier that ends the loop body)
             uint4* c4 = reinterpret_cast<uint4*>(cnt);
-            for (int i = tid; i < RS_WARPS * R / 4; i += RS_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < WARPS * R / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
             if (R < 4)
-                for (int i = tid; i < RS_WARPS * R; i += RS_THREADS) cnt[i] = 0;
+                for (int i = tid; i < WARPS * R; i += THREADS) cnt[i] = 0;
         }
         __syncthreads();
 
         KT key[ITEMS];
         unsigned rank[ITEMS / 2];  // two 16-bit slots per register (a slot is < TILE <= 65536)
-        static_assert(ITEMS % 8 == 0 && RS_THREADS * ITEMS <= 65536, "packed ranks, batches of eight");
+        static_assert(ITEMS % 8 == 0 && THREADS * ITEMS <= 65536, "packed ranks, batches of eight");
         const int seg = tile_begin + w * (32 * ITEMS);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -219,10 +222,10 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS >= 32 ? (sizeof(KT) == 4 ? R
         __syncthreads();
 
         // per digit: exclusive prefix over the warps; tile_off[d] temporarily holds the tile's digit count
-        for (int d = tid; d < R; d += RS_THREADS) {
+        for (int d = tid; d < R; d += THREADS) {
             unsigned run = 0;
 #pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ++ww) {
+            for (int ww = 0; ww < WARPS; ++ww) {
                 const unsigned t = cnt[ww * R + d];
                 cnt[ww * R + d] = run;
                 run += t;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(RS_THREADS, ITEMS >= 32 ? (sizeof(KT) == 4 ? R
         __syncthreads();
 
         const int tile_n = min(TILE, end - tile_begin);
-        for (int j = tid; j < tile_n; j += RS_THREADS) {
+        for (int j = tid; j < tile_n; j += THREADS) {
             const KT k = st_keys[j];
             const unsigned d = (unsigned)((k >> shift) & mask);
             const unsigned g = gbase[d] + ((unsigned)j - tile_off[d]);
@@ -559,10 +562,10 @@ inline cudaError_t rs_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_rs_scatter<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const int smem_big = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT), RS_ITEMS_BIG);
-    e = cudaFuncSetAttribute(k_rs_scatter<KT, true, RS_ITEMS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
+    const int smem_big = (int)rs_scatter_smem_bytes(RS_MAX_BITS, sizeof(KT), RS_ITEMS_BIG, RS_BIG_THREADS);
+    e = cudaFuncSetAttribute(k_rs_scatter<KT, true, RS_ITEMS_BIG, RS_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_rs_scatter<KT, false, RS_ITEMS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
+    return cudaFuncSetAttribute(k_rs_scatter<KT, false, RS_ITEMS_BIG, RS_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big);
 }
 
 // pass / chunk plan of the three-kernel path (shared with k_cell_keys_hist, which produces pass 0's histogram itself)
@@ -579,7 +582,7 @@ inline RsPlan rs_plan(int n, int key_bits, const RadixWorkspace& ws) {
     p.base = key_bits / p.passes;
     p.rem = key_bits % p.passes;
     p.big = ws.big_tile_from > 0 && n >= ws.big_tile_from;
-    p.ck = make_chunking(n, RS_THREADS * (p.big ? RS_ITEMS_BIG : RS_ITEMS), RS_MAX_GRID);
+    p.ck = make_chunking(n, p.big ? RS_BIG_TILE : RS_TILE, RS_MAX_GRID);
     p.bits0 = p.base + (0 < p.rem ? 1 : 0);
     return p;
 }
@@ -683,13 +686,13 @@ inline int radix_sort_pairs(cudaStream_t st, KT* k[2], uint32_t* v[2], int n, in
         prof.begin(kid_base + 1);
         k_rs_scan<<<(R + 7) / 8, 256, 0, st>>>(ws.hist, ws.prefix, ws.tot, R, ck.grid);
         prof.end();
-        const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT), big ? RS_ITEMS_BIG : RS_ITEMS);
+        const size_t smem = rs_scatter_smem_bytes(bits, sizeof(KT), big ? RS_ITEMS_BIG : RS_ITEMS, big ? RS_BIG_THREADS : RS_THREADS);
         prof.begin(kid_base + 2);
         if (p == 0 && iota_first) {
-            if (big) k_rs_scatter<KT, true, RS_ITEMS_BIG><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+            if (big) k_rs_scatter<KT, true, RS_ITEMS_BIG, RS_BIG_THREADS><<<ck.grid, RS_BIG_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
             else k_rs_scatter<KT, true><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
         } else {
-            if (big) k_rs_scatter<KT, false, RS_ITEMS_BIG><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
+            if (big) k_rs_scatter<KT, false, RS_ITEMS_BIG, RS_BIG_THREADS><<<ck.grid, RS_BIG_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
             else k_rs_scatter<KT, false><<<ck.grid, RS_THREADS, smem, st>>>(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, ck.chunk, shift, bits, ws.prefix, ws.tot);
         }
         prof.end();
