@@ -188,3 +188,46 @@ def test_pointcloud2_through_the_small_path(mot, oracle, synth):
     assert np.array_equal(out["offsets"], o_ref) and np.array_equal(out["indices"], i_ref)
     np.testing.assert_allclose(out["centroids"], oracle.get_centroid(kept_ref, o_ref, i_ref, 1.5), rtol=RTOL, atol=1e-6)
     t.close()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_chains_and_random_frames(mot, oracle, seed):
+    # shapes that stress the shared-memory union-find of k_fs_tables: long thin components (a spiral and a zig-zag whose points sit
+    # just under the tolerance apart: thousands of cells in ONE component, joined through chains of cell pairs), planes, blobs and
+    # noise, at sizes up to the path's limit of kept points; the small path must take every frame and agree with the oracle
+    rng = np.random.default_rng(1000 + seed)
+    tol = float(rng.choice([0.12, 0.2, 0.35, 0.5, 0.8]))
+    n_chain = int(rng.integers(500, 12000))
+    s = np.arange(n_chain, dtype=np.float64) * (tol * rng.uniform(0.55, 0.98))
+    ang = s / 6.0
+    spiral = np.stack([(4 + 0.3 * ang) * np.cos(ang), (4 + 0.3 * ang) * np.sin(ang), 0.02 * s], 1)
+    zz = np.stack([s % 37.0, 50 + (s // 37.0) * tol * 0.9, np.zeros_like(s)], 1)
+    n_plane = int(rng.integers(0, 9000))
+    plane = np.stack([rng.uniform(-60, -40, n_plane), rng.uniform(-10, 10, n_plane), np.full(n_plane, 1.5)], 1)
+    k = int(rng.integers(1, 40))
+    centres = rng.uniform(-30, 30, (k, 3))
+    n_blob = int(rng.integers(100, 15000))
+    blobs = centres[rng.integers(0, k, n_blob)] + rng.normal(0, tol * 0.8, (n_blob, 3))
+    n_noise = int(rng.integers(0, 3000))
+    noise = rng.uniform(-80, 80, (n_noise, 3))
+    pts = np.concatenate([spiral, zz, plane, blobs, noise]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    assert len(pts) <= 49152
+    cloud = np.zeros((len(pts), 4), np.float32)
+    cloud[:, :3] = pts
+    t = mot.Tracker(device=0, max_points=len(cloud), max_tracks=0)
+    t.small_frames(max_points=131072)
+    mn, mx = int(rng.choice([1, 3, 10])), int(rng.choice([200, 5000, 1 << 30]))
+    t.set_cluster_params(tol, mn, mx)
+    before = t.small_frames()
+    off, idx = t.extract(cloud)
+    after = t.small_frames()
+    lab = oracle.labels_grid(cloud, tol)
+    o_ref, i_ref = oracle.csr_from_labels(lab, mn, mx)
+    assert np.array_equal(t.result_labels(), lab), "component labels"
+    assert np.array_equal(off, o_ref) and np.array_equal(idx, i_ref), "CSR"
+    took_small = after[1] == before[1] + 1
+    crowded = np.unique(np.floor(pts.astype(np.float64) * (2.0 / (tol * (1 + 2.0 ** -10)))).astype(np.int64), axis=0, return_counts=True)[1].max() > 64
+    many = len(o_ref) - 1 > 4096
+    assert took_small or crowded or many or (after[2] > before[2]), "the frame neither took the small path nor was handed back"
+    t.close()
