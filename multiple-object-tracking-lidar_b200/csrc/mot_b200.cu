@@ -53,7 +53,7 @@ enum KernelId {
     KID_RS_COUNT, KID_RS_COMPACT, KID_BBOX, KID_KEYS, KID_SORT_HIST, KID_SORT_SCAN, KID_SORT_SCATTER, KID_CELLS_COUNT, KID_HASH_CLEAR, KID_CELLS_WRITE,
     KID_UF1, KID_FLATTEN1, KID_UF2, KID_FLATTEN2, KID_COARSE_REC, KID_UF_COARSE, KID_UF_DENSE1, KID_UF_DENSE, KID_COMP_ACC, KID_KEPT_LIST, KID_CL_SMALL, KID_CLSORT_HIST, KID_CLSORT_SCAN,
     KID_CLSORT_SCATTER, KID_CL_COUNT, KID_CL_FINALIZE, KID_FRAME_CL_OFF, KID_POINT_RANK, KID_PART_HIST, KID_PART_SCAN, KID_PART_SCATTER,
-    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_FS_FRONT, KID_FS_EDGES, KID_FS_TABLES, KID_FS_FARTHEST, KID_FS_FINISH, KID_N
+    KID_LOCALIZE, KID_STATS_INIT, KID_STATS, KID_STATS_FIN, KID_FARTHEST_PAIR, KID_CIRCUMCENTRE, KID_IHGP, KID_VOX_KEYS, KID_VOX_HIST, KID_VOX_SCAN, KID_VOX_SCATTER, KID_SEG_COUNT, KID_SEG_WRITE, KID_VOX_FIN, KID_PC2_UNPACK, KID_PC2_COMPACT, KID_ASSOCIATE, KID_TRACKS_PURGE, KID_UF_PAIR, KID_CELL_LOCAL, KID_UF_CROSS, KID_UF_HEAVY1, KID_FLATTEN_IF, KID_UF_HEAVY2, KID_UF_SURV, KID_UF_WALK, KID_UF_FUSED, KID_CSR_COMPACT, KID_CELL_LOCAL_DENSE, KID_HASH_BUILD, KID_FS_FRONT, KID_FS_EDGES, KID_FS_TABLES, KID_FS_FARTHEST, KID_FS_FINISH, KID_TRACKS_APPLY, KID_N
 };
 static const char* const kKernelNames[KID_N] = {
     "k_rs_count", "k_compact_onepass<map>", "k_bbox", "k_cell_keys", "k_rs_hist[cells]", "k_rs_scan[cells]", "k_rs_scatter[cells]", "k_cells_count",
@@ -61,7 +61,7 @@ static const char* const kKernelNames[KID_N] = {
     "k_clusters_small", "k_rs_hist[clusters]", "k_rs_scan[clusters]", "k_rs_scatter[clusters]", "k_clusters_count", "k_clusters_finalize",
     "k_frame_cluster_offsets", "k_point_rank", "k_rs_hist[csr]", "k_rs_scan[csr]", "k_rs_scatter[csr]", "k_localize_indices",
     "k_stats_init", "k_stats_accumulate", "k_stats_finalize", "k_farthest_pair", "k_circumcentre", "k_ihgp_step", "k_voxel_keys", "k_rs_hist[voxel]", "k_rs_scan[voxel]", "k_rs_scatter[voxel]",
-    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build", "k_fs_front", "k_fs_edges", "k_fs_tables", "k_fs_farthest", "k_fs_finish"};
+    "k_seg_count", "k_seg_write", "k_voxel_finalize", "k_pc2_unpack", "k_compact_onepass<finite>", "k_associate", "k_tracks_purge", "k_uf_sparse2", "k_cell_local", "k_uf_cross", "k_uf_heavy<1>", "k_uf_flatten_if", "k_uf_heavy<2>", "k_uf_survivors", "k_uf_walk", "k_uf_fused", "k_compact_keys_onepass", "k_cell_local_dense", "k_hash_build", "k_fs_front", "k_fs_edges", "k_fs_tables", "k_fs_farthest", "k_fs_finish", "k_tracks_apply"};
 
 struct mot_handle {
     int device = 0;
@@ -197,7 +197,9 @@ struct mot_handle {
     int* d_trk_ids[2] = {nullptr, nullptr};
     float4* d_trk_rings[2] = {nullptr, nullptr};
     double* d_trk_m[2] = {nullptr, nullptr};
-    int *d_trk_meta = nullptr, *d_trk_seen = nullptr, *d_ent_ids = nullptr, *d_ent_slot = nullptr, *d_ent_occ = nullptr;
+    int *d_trk_meta = nullptr, *d_trk_seen = nullptr, *d_ent_ids = nullptr, *d_ent_slot = nullptr, *d_ent_occ = nullptr, *d_ent_next = nullptr;
+    float4* d_ent_prev = nullptr;  // last observation an entry replaced (k_associate_fast -> k_tracks_apply)
+    int assoc_fast = 1;            // MOT_ASSOC_FAST=0: the one-kernel association (k_associate) for every table size
     float4* d_centroids_in = nullptr;
     int trk_cur = 0, trk_L = 0, trk_spin = 0, trk_n = 0;
     bool trk_first = true;
@@ -1259,6 +1261,9 @@ int mot_create(int device, size_t max_points, size_t max_tracks, mot_handle** ou
             CK(dalloc(&h->d_ent_ids, max_tracks));
             CK(dalloc(&h->d_ent_slot, max_tracks));
             CK(dalloc(&h->d_ent_occ, max_tracks));
+            CK(dalloc(&h->d_ent_next, max_tracks));
+            CK(dalloc(&h->d_ent_prev, max_tracks));
+            if (const char* e = getenv("MOT_ASSOC_FAST")) h->assoc_fast = atoi(e);
             CK(dalloc(&h->d_centroids_in, max_tracks));
         }
         return MOT_OK;
@@ -1283,7 +1288,7 @@ int mot_destroy(mot_handle* h) {
                     h->d_counts, h->d_bbox, h->d_frame_offsets, h->d_frame_offsets_in, h->d_frame_stamps, h->d_c1p_status, h->d_frame_cl_offsets, h->d_stats, h->d_statacc, h->d_crec, h->d_dense_list, h->d_nbr, h->d_centroids, h->d_cands, h->d_bits,
                     h->d_rings, h->d_mstate, h->d_posvel, h->d_track_ids, h->d_obstacles, h->d_raw, h->d_trk_ids[0], h->d_trk_ids[1],
                     h->d_trk_rings[0], h->d_trk_rings[1], h->d_trk_m[0], h->d_trk_m[1], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids, h->d_ent_slot,
-                    h->d_ent_occ, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2, h->d_fs_state, h->d_fs_args, h->d_fs_phase_ns};
+                    h->d_ent_occ, h->d_ent_next, h->d_ent_prev, h->d_centroids_in, h->d_ckey, h->d_fcode, h->d_tasks, h->d_cbox, h->d_fbox, h->d_heavy1, h->d_heavy2, h->d_fs_state, h->d_fs_args, h->d_fs_phase_ns};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -2167,6 +2172,19 @@ int mot_tracks_reset(mot_handle* h) {
     return MOT_OK;
 }
 
+// The double S with  float(sqrt(s)) < thr  <=>  s < S  for every s >= 0: both roundings are monotone, so the set of passing s is an
+// initial segment of the non-negative doubles, whose bit patterns are ordered like the values (bisection over the patterns).
+static double assoc_match_below(float thr) {
+    if (!(thr > 0.0f)) return 0.0;  // nothing is closer than a non-positive threshold (first frame: -1)
+    auto from_bits = [](uint64_t b) { double d; std::memcpy(&d, &b, sizeof(d)); return d; };
+    uint64_t lo = 0, hi = 0x7ff0000000000000ull;  // s = 0 passes, s = +inf does not
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if ((float)std::sqrt(from_bits(mid)) < thr) lo = mid; else hi = mid;
+    }
+    return from_bits(hi);
+}
+
 int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids, double now, float id_threshold, float frequency,
                     int32_t* this_obj_ids, float* pos_vel, mot_obstacle* obstacles, int32_t* n_tracks, int32_t* produced) {
     if (!h) return MOT_ERR_INVALID;
@@ -2196,9 +2214,27 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
     CK(cudaMemcpyAsync(h->d_centroids_in, centroids_xyzi, (size_t)K * 16, cudaMemcpyDefault, st));
     // first frame: every centroid registers a track, nothing is filtered or published (MOT.cpp:126-161)
     const float thr = h->trk_first ? -1.0f : id_threshold;
-    LAUNCH(KID_ASSOCIATE, k_associate<<<1, ASSOC_THREADS, 0, st>>>(h->d_centroids_in, K, L, (int)h->max_tracks, thr, dt_gp, h->d_trk_ids[cur],
-                                                                  h->d_trk_rings[cur], h->d_trk_m[cur], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids,
-                                                                  h->d_ent_slot, h->d_ent_occ));
+    if (h->assoc_fast && h->max_tracks <= (size_t)AF_MAX_TRACKS) {
+        // the sequential part against a shared-memory table of last observations, then everything a match implies in parallel
+        const int cap = (int)h->max_tracks;
+        const size_t smem = af_smem_bytes(cap);
+        // (the kernel also has ~6 KB of static shared memory: the opt-in is needed well below 48 KB of dynamic size)
+        CK(cudaFuncSetAttribute(k_associate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 16 * 1024)));
+        // CTA width by table size (barriers of a narrow CTA are cheaper): the table can grow by K inside the call
+        const int af_threads = std::min(ASSOC_THREADS, std::max(128, ((h->trk_n + K + 31) / 32) * 32));
+        LAUNCH(KID_ASSOCIATE, k_associate_fast<<<1, af_threads, smem, st>>>(h->d_centroids_in, K, L, cap, assoc_match_below(thr), h->d_trk_ids[cur], h->d_trk_rings[cur],
+                                                                              h->d_trk_meta, h->d_ent_slot, h->d_ent_occ, h->d_ent_next, h->d_trk_seen,
+                                                                              h->d_ent_prev, cap));
+        LAUNCH(KID_TRACKS_APPLY, k_tracks_apply<<<(K + TA_THREADS / 32 - 1) / (TA_THREADS / 32), TA_THREADS, 0, st>>>(
+                                     h->d_centroids_in, K, L, dt_gp, h->d_trk_ids[cur], h->d_trk_rings[cur], h->d_trk_m[cur], h->d_ent_slot, h->d_ent_occ,
+                                     h->d_ent_next, h->d_trk_seen, h->d_ent_prev, h->d_ent_ids));
+        CK(cudaGetLastError());  // a failed launch must not reach the host code that reads the table's counters
+    } else {
+        LAUNCH(KID_ASSOCIATE, k_associate<<<1, ASSOC_THREADS, 0, st>>>(h->d_centroids_in, K, L, (int)h->max_tracks, thr, dt_gp, h->d_trk_ids[cur],
+                                                                      h->d_trk_rings[cur], h->d_trk_m[cur], h->d_trk_meta, h->d_trk_seen, h->d_ent_ids,
+                                                                      h->d_ent_slot, h->d_ent_occ));
+    }
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_pinned + 32, h->d_trk_meta, TM_N * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(mot_sync(h));
     h->trk_n = h->h_pinned[32 + TM_NTRACKS];
@@ -2215,7 +2251,7 @@ int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids,
         return dropped ? MOT_WARN_TRACKS_FULL : MOT_OK;
     }
     // callIHGP over this_objIDs (MOT.cpp:621-662); a track that was matched twice in this frame is filtered twice, in order
-    const int max_occ = h->h_pinned[32 + TM_MAX_OCC];
+    const int max_occ = std::min(std::max(h->h_pinned[32 + TM_MAX_OCC], 0), K);  // (a track is matched at most K times in a frame)
     if (dropped) {
         CK(cudaMemsetAsync(h->d_posvel, 0, (size_t)K * 2 * sizeof(float4), st));
         CK(cudaMemsetAsync(h->d_obstacles, 0, (size_t)K * sizeof(ObstacleRow), st));

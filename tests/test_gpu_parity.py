@@ -438,13 +438,22 @@ def _tracker_scenario(seed, n_frames, n_obj, dt=0.1):
     return frames
 
 
-@pytest.mark.parametrize("seed,L", [(1, 10), (2, 40)])
-def test_tracks_association_lifecycle(mot, oracle, seed, L):
-    # cloudCallback's association / interpolation / registration / callIHGP / purge, device resident
+@pytest.mark.parametrize("seed,L,fast", [(1, 10, 1), (2, 40, 1), (2, 40, 0), (3, 7, 1), (4, 70, 1), (5, 33, 1)])
+def test_tracks_association_lifecycle(mot, oracle, seed, L, fast):
+    # cloudCallback's association / interpolation / registration / callIHGP / purge, device resident.
+    # fast = 1: k_associate_fast (shared-memory table of last observations) + k_tracks_apply; 0: the one-kernel k_associate
     from oracle.tracker_ref import TrackerRef
     hyp = (np.exp(-5.5), np.exp(-3.5), np.exp(0.75))
     freq, thr = 10.0, 0.4
-    t = mot.Tracker(device=0, max_points=1024, max_tracks=512)
+    saved = os.environ.get("MOT_ASSOC_FAST")
+    os.environ["MOT_ASSOC_FAST"] = str(fast)
+    try:
+        t = mot.Tracker(device=0, max_points=1024, max_tracks=512)
+    finally:
+        if saved is None:
+            os.environ.pop("MOT_ASSOC_FAST", None)
+        else:
+            os.environ["MOT_ASSOC_FAST"] = saved
     t.ihgp_configure(0.1, 0.03, hyp, hyp, L)
     ref = TrackerRef(freq, thr, L, 0.03, hyp, hyp)
     produced = 0
