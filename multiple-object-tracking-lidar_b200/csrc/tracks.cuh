@@ -122,6 +122,7 @@ constexpr int AF_CHUNK = 128;  // entries whose records are kept in shared memor
 // (correctly rounded sqrt and the conversion to float are both monotone), so it equals s < match_below for the one double the host
 // finds by bisection over the bit patterns (mot_b200.cu: assoc_match_below) -- no 64-bit square root on the critical path.
 __global__ void __launch_bounds__(ASSOC_THREADS, 1) k_associate_fast(const float4* __restrict__ centroids, int K, int L, int max_tracks, double match_below,
+                                                                      float f_lo, float f_hi,
                                                                       int* __restrict__ ids, const float4* __restrict__ rings, int* __restrict__ meta,
                                                                       int* __restrict__ slot_of_entry, int* __restrict__ occurrence,
                                                                       int* __restrict__ next_entry, int* __restrict__ entry_new,
@@ -168,11 +169,21 @@ __global__ void __launch_bounds__(ASSOC_THREADS, 1) k_associate_fast(const float
                 for (int t = tid; t < n; t += n_search) {
                     float4 last = s_last[t];
                     if (t == pend_slot) last = pend_obj;
-                    const double dx = __dsub_rn((double)obj.x, (double)last.x), dy = __dsub_rn((double)obj.y, (double)last.y);
-                    if (__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.0) < match_below) { best = t; break; }  // t ascending per thread
+                    // fp32 first: fl(a - b) is the correctly rounded difference, so fs is within 4 ulp-steps (2.4e-7 relative) of the
+                    // exact squared distance; outside the +-2e-6 band around the threshold the fp64 value falls on the same side.  The
+                    // band itself (and NaN) takes the reference's double expression -- five dependent fp64 operations that otherwise sit
+                    // on the critical path of every centroid (ncu: the step is a latency chain, not issue bound)
+                    const float fx = __fsub_rn(obj.x, last.x), fy = __fsub_rn(obj.y, last.y);
+                    const float fs = __fadd_rn(__fmul_rn(fx, fx), __fmul_rn(fy, fy));
+                    if (fs > f_hi) continue;
+                    if (!(fs < f_lo)) {
+                        const double dx = __dsub_rn((double)obj.x, (double)last.x), dy = __dsub_rn((double)obj.y, (double)last.y);
+                        if (!(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), 0.0) < match_below)) continue;
+                    }
+                    best = t;  // t ascending per thread
+                    break;
                 }
-                best = __reduce_min_sync(kFull, best);
-                if (lane_id() == 0 && best != 0x7fffffff) atomicMin(&s_min[step], best);
+                if (best != 0x7fffffff) atomicMin(&s_min[step], best);  // (the compiler aggregates the warp's lanes: one redux + one shared-memory atomic)
             }
             __syncthreads();
             const int b = s_min[step];
