@@ -461,6 +461,12 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_configs:
         import bench_configs
         out["configs"] = bench_configs.run(mot, entry.load_oracle(), local_rank, peak, quick=args.quick_configs)
+        c1 = out["configs"].get("c1", {})
+        # the reference's own frame shape (c1: 65,536 points + map) beside the 2^20-point figure above: CUDA events around the call, and
+        # first-to-last kernel instruction on the device
+        out["small_frame_latency_us"] = {"around_call": round(c1["ms"] * 1e3, 1) if "ms" in c1 else None, "on_device": c1.get("device_us"),
+                                         "host_buffers": round(c1["host_buffers_ms"] * 1e3, 1) if "host_buffers_ms" in c1 else None,
+                                         "workload": "c1 frame, removeStatic + clustering + tables + circumcentres"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(frames_np[0], p)
     for t_ in trks:
