@@ -287,6 +287,11 @@ int mot_ihgp_step_obstacles(mot_handle* h, const float* rings, int n_tracks, con
  * first frame: every centroid registers a track and *produced = 0 (nothing is filtered or published, MOT.cpp:126-161).
  * Outputs per centroid: this_obj_ids, pos_vel (8 floats, as mot_ihgp_step) and optionally the obstacle table. */
 int mot_tracks_reset(mot_handle* h);
+/* Test aid (host only, no device needed): the double S for which the reference's association test
+ * (float)sqrt(dx*dx + dy*dy + 0) < id_threshold (euc_dist, MOT.cpp:1025-1028, used at :184-207) equals  dx*dx + dy*dy + 0 < S.
+ * Both roundings are monotone, so S exists and is found by bisection over the bit patterns; the device compares against it
+ * instead of taking a 64-bit square root per track (csrc/tracks.cuh). */
+double mot_assoc_match_below(float id_threshold);
 int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids, double now, float id_threshold,
                     float frequency, int32_t* this_obj_ids, float* pos_vel, mot_obstacle* obstacles, int32_t* n_tracks,
                     int32_t* produced);

@@ -87,6 +87,7 @@ SYMBOLS = {
     "mot_unpack_pointcloud2": (C.c_int, [_H, C.c_void_p, _SIZE, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, _SIZE,
                                          C.POINTER(_SIZE)]),
     "mot_tracks_reset": (C.c_int, [_H]),
+    "mot_assoc_match_below": (C.c_double, [C.c_float]),
     "mot_tracks_step": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]),
     "mot_tracks_get": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, _SIZE, C.POINTER(C.c_int32)]),

@@ -2185,6 +2185,8 @@ static double assoc_match_below(float thr) {
     return from_bits(hi);
 }
 
+double mot_assoc_match_below(float id_threshold) { return assoc_match_below(id_threshold); }
+
 int mot_tracks_step(mot_handle* h, const float* centroids_xyzi, int n_centroids, double now, float id_threshold, float frequency,
                     int32_t* this_obj_ids, float* pos_vel, mot_obstacle* obstacles, int32_t* n_tracks, int32_t* produced) {
     if (!h) return MOT_ERR_INVALID;

@@ -79,3 +79,23 @@ def test_synthetic_generators_are_deterministic(synth):
     sc = synth.scene_c3()
     f = sc.frame(3, n_points=synth.C3_POINTS)
     assert f.shape == (synth.C3_POINTS, 4) and np.isfinite(f).all()
+
+
+def test_assoc_threshold_is_exact(mot):
+    # the association kernel replaces the reference's  float(sqrt(dx^2 + dy^2 + 0)) < id_threshold  (MOT.cpp:1025-1028, :184-207) by
+    # s < S with S from mot_assoc_match_below: the two must agree for EVERY double s, in particular on both sides of the boundary
+    import struct
+    lib = mot.load()
+    rng = np.random.default_rng(11)
+    thresholds = [0.4, 1.0, 0.1, 2.5, 1e-3, 1e-12, 7e5, float(np.float32(0.30000001))] + list(rng.uniform(0.01, 5.0, 40))
+    for thr in thresholds:
+        t = np.float32(thr)
+        S = lib.mot_assoc_match_below(float(t))
+        bits = struct.unpack("<Q", struct.pack("<d", S))[0]
+        near = np.array([struct.unpack("<d", struct.pack("<Q", bits + d))[0] for d in range(-300, 300)], dtype=np.float64)
+        s = np.concatenate([near, rng.uniform(0.0, 2.0 * float(t) ** 2, 4000), [0.0, np.inf, np.nan]])
+        with np.errstate(invalid="ignore", over="ignore"):
+            ref = np.sqrt(s).astype(np.float32) < t
+        assert np.array_equal(ref, s < S), thr
+    for thr in (0.0, -1.0):  # the first frame runs with -1: nothing matches
+        assert lib.mot_assoc_match_below(thr) == 0.0
